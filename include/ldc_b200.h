@@ -1,0 +1,153 @@
+/*
+ * ldc_b200.h -- C-ABI of the B200-native `cuda` backend for the coupled lid-driven-cavity
+ * solve (shared library lid_driven_cavity_problem_b200/csrc/libldc_b200.so, sm_100a).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - Every pointer named *_dev is DEVICE memory owned by the caller (the Python host keeps
+ *     them in torch tensors and passes tensor.data_ptr()).  The library owns only opaque
+ *     handles (ldc_solver*).
+ *   - Every call is stream-ordered on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream) and returns immediately unless stated otherwise.
+ *   - Return value: 0 = ok, <0 = error (ldc_last_error() gives the text).  No exception
+ *     crosses the ABI.  One host thread per handle.
+ *
+ * Unknown vector layout (reference: residual_function/pure_python_residual_function.py:10-22,
+ * nonlinear_solver/_common.py:4-18): cell c = i + nx*j, X[3c]=P, X[3c+1]=U (east face; dummy
+ * when i==nx-1), X[3c+2]=V (north face; dummy when j==ny-1).  Residual rows use the same slots.
+ */
+#ifndef LDC_B200_H
+#define LDC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDC_API __attribute__((visibility("default")))
+
+#define LDC_OK 0
+#define LDC_ERR_INVALID (-1)
+#define LDC_ERR_CUDA (-2)
+#define LDC_ERR_ALLOC (-3)
+#define LDC_ERR_STATE (-4)
+
+/* Description of the grid one call works on.  Replaces the attribute reads the reference's
+ * native residual does on the Python `graph` (c++/residual_function.cpp:16-43). */
+typedef struct ldc_grid {
+    int32_t nx, ny;          /* global cavity grid (pressure mesh), nx >= 3, ny >= 2          */
+    int32_t row_begin;       /* first grid row owned by this call (row-strip decomposition)  */
+    int32_t row_count;       /* rows owned; full grid: row_begin=0,row_count=ny              */
+    int32_t batch;           /* independent cavities stored back to back (Reynolds ensemble) */
+    int32_t use_cds;         /* central differencing instead of upwind (graph.use_cds)       */
+    double dt, dx, dy, rho, mi, bc;
+    const double *dt_dev;    /* optional per-instance dt[batch] (device); NULL -> dt          */
+    const double *bc_dev;    /* optional per-instance lid speed bc[batch] (device); NULL -> bc */
+} ldc_grid;
+
+/* Strip layout: X_dev/F_dev point at the first OWNED row; when row_begin > 0 the row below
+ * (ghost) lives at X_dev - 3*nx, when row_begin+row_count < ny the row above lives at
+ * X_dev + 3*nx*row_count.  U_old/V_old hold owned rows only: U_old[i + (nx-1)*jl],
+ * V_old[i + nx*jl] with jl the local row.  Instance b of a batch starts at
+ * b*3*nx*(row_count) (+ ghosts are not supported together with batch>1). */
+
+LDC_API const char *ldc_last_error(void);
+LDC_API int ldc_version(void);
+/* number of SMs etc. of the current device; returns 0 or error */
+LDC_API int ldc_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, int64_t *l2_bytes);
+
+/* ---- residual: replaces residual_function(X, graph) of c++/residual_function.cpp:10-238 and
+ * the five sibling backends.  F_dev is fully overwritten (dummy rows F=X).  When
+ * norm2_dev != NULL, *norm2_dev receives sum(F^2) per instance ([batch] doubles), computed by a
+ * deterministic two-stage reduction (work_dev must then hold ldc_residual_work_doubles()).
+ * variant: 0 = auto, 1 = cell-per-thread reference kernel, 2 = flux-form column-marching kernel.
+ */
+LDC_API int64_t ldc_residual_work_doubles(const ldc_grid *g);
+LDC_API int ldc_residual(const ldc_grid *g, const double *X_dev, const double *U_old_dev,
+                 const double *V_old_dev, double *F_dev, double *norm2_dev, double *work_dev,
+                 int32_t variant, void *stream);
+
+/* ---- packing: replaces _create_X / _recover_X (nonlinear_solver/_common.py:4-36) */
+LDC_API int ldc_pack_X(const ldc_grid *g, const double *U_dev, const double *V_dev, const double *P_dev,
+               double *X_dev, void *stream);
+LDC_API int ldc_unpack_X(const ldc_grid *g, const double *X_dev, double *U_dev, double *V_dev,
+                 double *P_dev, void *stream);
+
+/* ---- Jacobian mask: replaces _calculate_jacobian_mask (nonlinear_solver/_common.py:39-57).
+ * Canonical CSR (sorted, int32) of diags(7) (x) ones(dof,dof), wrap-around entries included. */
+LDC_API int64_t ldc_mask_nnz(int32_t nx, int32_t ny, int32_t dof);
+LDC_API int ldc_mask_csr(int32_t nx, int32_t ny, int32_t dof, int32_t *indptr_dev, int32_t *indices_dev,
+                 void *stream);
+
+/* ---- coloured finite-difference Jacobian: replaces SNESComputeJacobianDefaultColor +
+ * MatFDColoringApply ('ds') as configured by petsc_solver_wrapper.py:132,140.  One launch
+ * evaluates every colour; values_dev[nnz] is the CSR data array of the mask above
+ * (per instance: batch*nnz).  Full-grid only (row_begin=0,row_count=ny) in this version. */
+LDC_API int ldc_fd_jacobian(const ldc_grid *g, const double *X_dev, const double *U_old_dev,
+                    const double *V_old_dev, double *values_dev, void *stream);
+
+/* ---- SpMV y = J x on the mask pattern: replaces MatMult_SeqAIJ.
+ * ldc_spmv_mask uses the closed-form structure (no index arrays are read);
+ * ldc_spmv_csr is the canonical CSR product (reads indptr/indices). */
+LDC_API int ldc_spmv_mask(const ldc_grid *g, const double *values_dev, const double *x_dev, double *y_dev,
+                  void *stream);
+LDC_API int ldc_spmv_csr(int64_t n_rows, const int32_t *indptr_dev, const int32_t *indices_dev,
+                 const double *values_dev, const double *x_dev, double *y_dev, void *stream);
+
+/* ---- device-resident Newton-Krylov solve of one pseudo-time step and the time stepper.
+ * Replaces PetscSolverWrapper.solve/_setup_snes/_setup_options
+ * (nonlinear_solver/petsc_solver_wrapper.py:35-145) and the loop of
+ * time_stepper.run_simulation (time_stepper.py:9-56). */
+typedef struct ldc_solver ldc_solver;
+
+typedef struct ldc_solver_options {
+    double snes_rtol, snes_atol, snes_stol;   /* 1e-4 each  (petsc_solver_wrapper.py:135) */
+    int32_t snes_max_it;                      /* 50 */
+    int32_t snes_max_funcs;                   /* 10000 (PETSc default) */
+    double ksp_rtol, ksp_atol, ksp_dtol;      /* 1e-5, 1e-50, 1e5 (PETSc KSP defaults) */
+    int32_t ksp_max_it;                       /* 10000 */
+    int32_t gmres_restart;                    /* 30 */
+    int32_t pc_type;                          /* LDC_PC_* */
+    int32_t pc_sweeps;                        /* smoothing sweeps per level / per application */
+    int32_t mg_levels;                        /* 0 = auto (coarsen while both sizes are even) */
+    double pc_omega_u, pc_omega_p;            /* damping of the cell-block relaxation */
+    int32_t residual_variant;                 /* as in ldc_residual */
+    int32_t reserved;
+} ldc_solver_options;
+
+#define LDC_PC_NONE 0
+#define LDC_PC_VANKA 1      /* additive cell-block (pressure + 4 face velocities) relaxation */
+#define LDC_PC_MG_VANKA 2   /* geometric multigrid V-cycle smoothed by LDC_PC_VANKA */
+
+LDC_API void ldc_solver_default_options(ldc_solver_options *opt);
+
+/* result of one Newton solve, per instance; reason codes are PETSc's SNESConvergedReason as
+ * tabulated in petsc_solver_wrapper.py:12-31 (2,3,4 converged; -2..-5 diverged). */
+typedef struct ldc_newton_report {
+    int32_t reason;
+    int32_t iterations;
+    int32_t function_evaluations;
+    int32_t linear_iterations;
+    int32_t ksp_reason;
+    int32_t reserved;
+    double fnorm0, fnorm, xnorm, ynorm;
+} ldc_newton_report;
+
+LDC_API int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *opt, ldc_solver **out);
+LDC_API void ldc_solver_destroy(ldc_solver *s);
+/* device pointer of the interleaved state X (3*nx*ny*batch doubles), owned by the solver */
+LDC_API double *ldc_solver_state_dev(ldc_solver *s);
+/* set per-instance dt (host array of `batch` doubles) */
+LDC_API int ldc_solver_set_dt(ldc_solver *s, const double *dt_host);
+/* One pseudo-time step for every ACTIVE instance: X_old <- X, Newton solve, X <- solution.
+ * active_host[batch] (NULL = all) selects instances; diverged instances keep X = X_old.
+ * reports_host[batch] is filled.  Synchronises the stream before returning.
+ * du_inf_host[batch] (nullable) receives max|U - U_old| (steady-state test, time_stepper.py:39). */
+LDC_API int ldc_solver_step(ldc_solver *s, const int32_t *active_host, ldc_newton_report *reports_host,
+                    double *du_inf_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDC_B200_H */

@@ -1,0 +1,227 @@
+// Jacobian sparsity mask and coloured finite-difference Jacobian on the device (sm_100a).
+//
+// ldc_mask_csr    replaces _calculate_jacobian_mask (nonlinear_solver/_common.py:39-57): the
+//                 canonical CSR of diags(ones(7), [-nx+1,-nx,-1,0,1,nx,nx-1]) (x) ones(dof,dof)
+//                 from its closed form (MaskGeom), wrap-around entries included, bit-exact.
+// ldc_fd_jacobian replaces PETSc's SNESComputeJacobianDefaultColor / MatFDColoringApply with
+//                 mat_fd_type 'ds' (petsc_solver_wrapper.py:132,140).  PETSc needs >= 21
+//                 residual sweeps (one per colour).  Here ONE launch evaluates every colour:
+//                 a residual row depends on at most one unknown of each colour, so
+//                 F_r(x + sum_{c in colour} h_c e_c) == F_r(x + h_c e_c) bit for bit, and each
+//                 thread perturbs the stencil values of its own three rows in registers.
+//                 Entries whose unknown the row never reads (dummy slots, wall-substituted
+//                 neighbours, the mask's wrap-around pairs, the 37 structural zeros per cell)
+//                 are exactly 0.0, which is what the column-by-column difference gives.
+//                 The values land in the CSR data array of the mask (staged through shared
+//                 memory so the global writes are fully coalesced).
+#include "ldc_internal.cuh"
+
+namespace ldc {
+
+// ---------------------------------------------------------------------------------------------
+// mask
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mask_csr_kernel(int nx, int ny, int dof, int32_t *__restrict__ indptr, int32_t *__restrict__ indices)
+{
+    const MaskGeom m{nx, (long)nx * ny};
+    const long rows = m.N * dof;
+    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > rows) return;
+    if (r == rows) {
+        indptr[rows] = (int32_t)((long)dof * dof * m.pairs_before(m.N));
+        return;
+    }
+    const long c = r / dof;
+    const int d = (int)(r - c * dof);
+    const int lo = m.lo_missing(c), cnt = m.count(c);
+    const long start = (long)dof * dof * m.pairs_before(c) + (long)d * dof * cnt;
+    indptr[r] = (int32_t)start;
+    for (int k = 0; k < cnt; ++k) {
+        const long cc = c + m.offset(lo + k);
+        for (int e = 0; e < dof; ++e) indices[start + (long)k * dof + e] = (int32_t)(cc * dof + e);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// finite-difference Jacobian
+// ---------------------------------------------------------------------------------------------
+static constexpr int kFdCells = 64;  // cells (threads) per block
+
+// PETSc MatFDColoring 'ds': dx = x; |dx| < umin -> +-umin; dx *= error_rel
+__device__ __forceinline__ double fd_step(double x)
+{
+    const double umin = 1.0e-6, eps = 1.4901161193847656e-08;
+    double h = x;
+    if (fabs(h) < umin) h = (h >= 0.0) ? umin : -umin;
+    return dmul(h, eps);
+}
+
+// (F(x + h e) - F(x)) * (1/h) with the row formula evaluated on a perturbed copy of the stencil
+#define LDC_FD(ROWFN, BASE, FIELD, ACTIVE, F0, OUT)                          \
+    do {                                                                     \
+        OUT = 0.0;                                                           \
+        if (ACTIVE) {                                                        \
+            auto t__ = BASE;                                                 \
+            const double h__ = fd_step(t__.FIELD);                           \
+            t__.FIELD = dadd(t__.FIELD, h__);                                \
+            OUT = dmul(dsub(ROWFN(t__, p), F0), ddiv(1.0, h__));             \
+        }                                                                    \
+    } while (0)
+
+template <bool POW2>
+__global__ void __launch_bounds__(kFdCells)
+fd_jacobian_kernel(const ldc_grid g, const double *__restrict__ X,
+                   const double *__restrict__ U_old, const double *__restrict__ V_old,
+                   double *__restrict__ values, long nnz)
+{
+    __shared__ double stage[kFdCells * 63];
+
+    const int inst = blockIdx.y;
+    const int nx = g.nx, ny = g.ny;
+    const long N = (long)nx * ny;
+    X += inst * 3 * N;
+    U_old += inst * (long)(nx - 1) * ny;
+    V_old += inst * (long)nx * (ny - 1);
+    values += inst * nnz;
+    const Phys p = make_phys(g, inst);
+    const GridView gv{X, nx, ny, 0};
+    const MaskGeom m{nx, N};
+
+    const long c0 = (long)blockIdx.x * kFdCells;
+    const long c1 = (c0 + kFdCells < N) ? c0 + kFdCells : N;
+    const long chunk_base = m.row_start(c0, 0);
+    const int chunk_len = (int)(m.row_start(c1, 0) - chunk_base);  // row_start(N,0) == nnz
+
+    for (int t = threadIdx.x; t < chunk_len; t += kFdCells) stage[t] = 0.0;
+    __syncthreads();
+
+    const long c = c0 + threadIdx.x;
+    if (c < c1) {
+        const int j = (int)(c / nx), i = (int)(c - (long)j * nx);
+        const int lo = m.lo_missing(c), cnt = m.count(c);
+        double *row0 = stage + (m.row_start(c, 0) - chunk_base);
+        double *row1 = row0 + 3 * cnt;
+        double *row2 = row1 + 3 * cnt;
+        // slot of (offset k, dof e) inside a row; only called for offsets that exist
+        auto at = [&](int k, int e) { return 3 * (k - lo) + e; };
+        const bool W = i > 0, E = i < nx - 1, S = j > 0, Nn = j < ny - 1;
+
+        // ---- continuity row: linear, 4 dependencies (residual_function.cpp:77-84)
+        {
+            const double Ue = gv.U(i, j), Uw = gv.U(i - 1, j), Vn = gv.V(i, j), Vs = gv.V(i, j - 1);
+            const double f0 = cont_row(Ue, Uw, Vn, Vs, p);
+            if (E) {
+                const double h = fd_step(Ue);
+                row0[at(3, 1)] = dmul(dsub(cont_row(dadd(Ue, h), Uw, Vn, Vs, p), f0), ddiv(1.0, h));
+            }
+            if (W) {
+                const double h = fd_step(Uw);
+                row0[at(2, 1)] = dmul(dsub(cont_row(Ue, dadd(Uw, h), Vn, Vs, p), f0), ddiv(1.0, h));
+            }
+            if (Nn) {
+                const double h = fd_step(Vn);
+                row0[at(3, 2)] = dmul(dsub(cont_row(Ue, Uw, dadd(Vn, h), Vs, p), f0), ddiv(1.0, h));
+            }
+            if (S) {
+                const double h = fd_step(Vs);
+                row0[at(0, 2)] = dmul(dsub(cont_row(Ue, Uw, Vn, dadd(Vs, h), p), f0), ddiv(1.0, h));
+            }
+        }
+
+        // ---- x-momentum row of U[i,j] (or the dummy row F = X)
+        if (E) {
+            XmomIn s;
+            gather_xmom(gv, i, j, p.bc, __ldg(U_old + i + (long)(nx - 1) * j), s);
+            const double f0 = xmom_row<POW2>(s, p);
+            const bool E2 = i < nx - 2;  // U[i+1,j] is a real unknown
+            double v;
+            LDC_FD(xmom_row<POW2>, s, U_P, true, f0, v);  row1[at(3, 1)] = v;
+            LDC_FD(xmom_row<POW2>, s, P_w, true, f0, v);  row1[at(3, 0)] = v;
+            LDC_FD(xmom_row<POW2>, s, P_e, true, f0, v);  row1[at(4, 0)] = v;
+            LDC_FD(xmom_row<POW2>, s, U_W, W, f0, v);     if (W) row1[at(2, 1)] = v;
+            LDC_FD(xmom_row<POW2>, s, U_E, E2, f0, v);    if (E2) row1[at(4, 1)] = v;
+            LDC_FD(xmom_row<POW2>, s, U_N, Nn, f0, v);    if (Nn) row1[at(6, 1)] = v;
+            LDC_FD(xmom_row<POW2>, s, U_S, S, f0, v);     if (S) row1[at(0, 1)] = v;
+            LDC_FD(xmom_row<POW2>, s, V_NW, Nn, f0, v);   if (Nn) row1[at(3, 2)] = v;
+            LDC_FD(xmom_row<POW2>, s, V_NE, Nn, f0, v);   if (Nn) row1[at(4, 2)] = v;
+            LDC_FD(xmom_row<POW2>, s, V_SW, S, f0, v);    if (S) row1[at(0, 2)] = v;
+            LDC_FD(xmom_row<POW2>, s, V_SE, S, f0, v);    if (S) row1[at(1, 2)] = v;
+        } else {
+            const double x = X[3 * c + 1];
+            const double h = fd_step(x);
+            row1[at(3, 1)] = dmul(dsub(dadd(x, h), x), ddiv(1.0, h));
+        }
+
+        // ---- y-momentum row of V[i,j] (or the dummy row)
+        if (Nn) {
+            YmomIn s;
+            gather_ymom(gv, i, j, p.bc, __ldg(V_old + c), s);
+            const double f0 = ymom_row<POW2>(s, p);
+            const bool N2 = j < ny - 2;  // V[i,j+1] / U[.,j+1] are read (not the lid quirk)
+            double v;
+            LDC_FD(ymom_row<POW2>, s, V_P, true, f0, v);      row2[at(3, 2)] = v;
+            LDC_FD(ymom_row<POW2>, s, P_s, true, f0, v);      row2[at(3, 0)] = v;
+            LDC_FD(ymom_row<POW2>, s, P_n, true, f0, v);      row2[at(6, 0)] = v;
+            LDC_FD(ymom_row<POW2>, s, V_E, E, f0, v);         if (E) row2[at(4, 2)] = v;
+            LDC_FD(ymom_row<POW2>, s, V_W, W, f0, v);         if (W) row2[at(2, 2)] = v;
+            LDC_FD(ymom_row<POW2>, s, V_N, N2, f0, v);        if (N2) row2[at(6, 2)] = v;
+            LDC_FD(ymom_row<POW2>, s, V_S, S, f0, v);         if (S) row2[at(0, 2)] = v;
+            LDC_FD(ymom_row<POW2>, s, U_SE, E, f0, v);        if (E) row2[at(3, 1)] = v;
+            LDC_FD(ymom_row<POW2>, s, U_SW, W, f0, v);        if (W) row2[at(2, 1)] = v;
+            LDC_FD(ymom_row<POW2>, s, U_NE, E && N2, f0, v);  if (E && N2) row2[at(6, 1)] = v;
+            LDC_FD(ymom_row<POW2>, s, U_NW, W && N2, f0, v);  if (W && N2) row2[at(5, 1)] = v;
+        } else {
+            const double x = X[3 * c + 2];
+            const double h = fd_step(x);
+            row2[at(3, 2)] = dmul(dsub(dadd(x, h), x), ddiv(1.0, h));
+        }
+    }
+    __syncthreads();
+    // the block's CSR values are one contiguous global range: coalesced copy-out
+    double *out = values + chunk_base;
+    for (int t = threadIdx.x; t < chunk_len; t += kFdCells) out[t] = stage[t];
+}
+
+}  // namespace ldc
+
+using namespace ldc;
+
+extern "C" int64_t ldc_mask_nnz(int32_t nx, int32_t ny, int32_t dof)
+{
+    if (nx < 3 || ny < 1 || dof < 1) return -1;
+    const MaskGeom m{nx, (long)nx * ny};
+    return (int64_t)dof * dof * m.pairs_before(m.N);
+}
+
+extern "C" int ldc_mask_csr(int32_t nx, int32_t ny, int32_t dof, int32_t *indptr_dev,
+                            int32_t *indices_dev, void *stream)
+{
+    LDC_REQUIRE(nx >= 3 && ny >= 1 && dof >= 1, "ldc_mask_csr: need nx>=3, ny>=1, dof>=1");
+    LDC_REQUIRE(indptr_dev && indices_dev, "ldc_mask_csr: null device pointer");
+    const int64_t nnz = ldc_mask_nnz(nx, ny, dof);
+    LDC_REQUIRE(nnz < 2147483647LL, "ldc_mask_csr: nnz=%lld does not fit the int32 CSR of the reference",
+                (long long)nnz);
+    const long rows = (long)nx * ny * dof + 1;
+    mask_csr_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        nx, ny, dof, indptr_dev, indices_dev);
+    LDC_CHECK_LAUNCH();
+    return LDC_OK;
+}
+
+extern "C" int ldc_fd_jacobian(const ldc_grid *g, const double *X_dev, const double *U_old_dev,
+                               const double *V_old_dev, double *values_dev, void *stream)
+{
+    if (int rc = validate_grid(g, true)) return rc;
+    LDC_REQUIRE(X_dev && U_old_dev && V_old_dev && values_dev, "ldc_fd_jacobian: null device pointer");
+    const long N = (long)g->nx * g->ny;
+    const long nnz = ldc_mask_nnz(g->nx, g->ny, 3);
+    dim3 grid((unsigned)((N + kFdCells - 1) / kFdCells), g->batch);
+    const bool pow2 = is_pow2_double(g->dx) && is_pow2_double(g->dy);
+    if (pow2)
+        fd_jacobian_kernel<true><<<grid, kFdCells, 0, (cudaStream_t)stream>>>(*g, X_dev, U_old_dev, V_old_dev, values_dev, nnz);
+    else
+        fd_jacobian_kernel<false><<<grid, kFdCells, 0, (cudaStream_t)stream>>>(*g, X_dev, U_old_dev, V_old_dev, values_dev, nnz);
+    LDC_CHECK_LAUNCH();
+    return LDC_OK;
+}

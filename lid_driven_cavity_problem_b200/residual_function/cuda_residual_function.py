@@ -1,0 +1,89 @@
+"""``residual_function(X, graph)`` on the B200 -- the `cuda` sibling of the reference's
+numpy / numba / Cython / C++ / C++-OpenMP residual modules
+(residual_function/cpp_residual_function.py:1-8 forwards to c++/residual_function.cpp:10).
+
+Contract: pure (neither X nor graph is modified), returns a freshly allocated
+length-3*nx*ny float64 vector.  ``X`` may be
+
+* a numpy array / sequence (what PETSc's callback and scipy's fsolve pass,
+  petsc_solver_wrapper.py:42-48, scipy_solver_wrapper.py:35): it is copied to the device
+  through pinned staging buffers, the kernel runs, and a numpy array comes back;
+* a CUDA ``torch.Tensor`` (float64): the result is a CUDA tensor and nothing crosses PCIe.
+
+Reads exactly what the reference's native residual reads from ``graph``
+(c++/residual_function.cpp:16-43): dt, dx, dy, rho, mi, bc, the mesh sizes and the
+``phi_old`` arrays of the U and V meshes (+ ``use_cds``, numba_residual_function.py:247).
+Unlike the C++ module, which reinterprets whatever buffer it is given as float64
+(SURVEY App. G), X is validated and converted to C-contiguous float64.
+"""
+import numpy as np
+
+from lid_driven_cavity_problem_b200 import _native
+
+try:
+    _native.load_library()
+except RuntimeError:
+    raise RuntimeError("CUDA module is not compiled.")
+
+_staging = {}
+
+
+def _pinned(name, n, torch):
+    key = (name, n)
+    buf = _staging.get(key)
+    if buf is None:
+        if len(_staging) > 16:
+            _staging.clear()
+        buf = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        _staging[key] = buf
+    return buf
+
+
+def _to_device(name, host, n, torch):
+    """host array -> device tensor through a cached pinned buffer"""
+    arr = np.ascontiguousarray(host, dtype=np.float64).reshape(-1)
+    if arr.size != n:
+        raise ValueError("%s has %d entries, expected %d" % (name, arr.size, n))
+    pin = _pinned(name, n, torch)
+    pin.numpy()[:] = arr
+    return pin.to('cuda', non_blocking=True)
+
+
+def residual_function_device(X_dev, graph, U_old_dev=None, V_old_dev=None, out=None, variant=0,
+                             norm2_out=None, batch=1):
+    """Device-to-device evaluation; every argument already lives in HBM."""
+    torch = _native.require_cuda()
+    lib = _native.lib()
+    nx, ny = int(graph.pressure_mesh.nx), int(graph.pressure_mesh.ny)
+    n = 3 * nx * ny * batch
+    if X_dev.dtype != torch.float64 or not X_dev.is_cuda or X_dev.numel() != n:
+        raise ValueError("X must be a CUDA float64 tensor of %d entries" % n)
+    X_dev = X_dev.contiguous()
+    if U_old_dev is None:
+        U_old_dev = _to_device('U_old', graph.ns_x_mesh.phi_old, (nx - 1) * ny * batch, torch)
+    if V_old_dev is None:
+        V_old_dev = _to_device('V_old', graph.ns_y_mesh.phi_old, nx * (ny - 1) * batch, torch)
+    F = torch.empty_like(X_dev) if out is None else out
+    g = _native.grid_from_graph(graph, batch=batch)
+    work = None
+    if norm2_out is not None:
+        work = torch.empty(int(lib.ldc_residual_work_doubles(g)), dtype=torch.float64, device='cuda')
+    rc = lib.ldc_residual(g, _native.ptr(X_dev), _native.ptr(U_old_dev), _native.ptr(V_old_dev),
+                          _native.ptr(F), _native.ptr(norm2_out), _native.ptr(work), variant,
+                          _native.current_stream())
+    _native.check(rc, 'ldc_residual')
+    return F
+
+
+def residual_function(X, graph):
+    torch = _native.require_cuda()
+    if isinstance(X, torch.Tensor):
+        return residual_function_device(X, graph)
+    nx, ny = int(graph.pressure_mesh.nx), int(graph.pressure_mesh.ny)
+    n = 3 * nx * ny
+    X_dev = _to_device('X', X, n, torch)
+    F_dev = residual_function_device(X_dev, graph)
+    out = _pinned('F', n, torch)
+    out.copy_(F_dev, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return out.numpy().copy()

@@ -1,0 +1,56 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/ldc_b200.h declares (no compute calls: there is no GPU in the build container)."""
+import os
+import re
+
+import pytest
+
+from conftest import REPO
+
+
+def _declared_symbols():
+    text = open(os.path.join(REPO, 'include', 'ldc_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(ldc_[A-Za-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from lid_driven_cavity_problem_b200 import _native
+    lib = _native.load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 12
+    for name in declared:
+        assert hasattr(lib, name), "libldc_b200.so does not export %s" % name
+    bound = set(_native.SYMBOLS)
+    assert bound == set(declared), (bound ^ set(declared))
+    assert lib.ldc_version() >= 100
+
+
+def test_mask_nnz_closed_form_host_side():
+    from lid_driven_cavity_problem_b200 import _native
+    lib = _native.load_library()
+    assert lib.ldc_mask_nnz(1024, 1024, 3) == 66023424
+    assert lib.ldc_mask_nnz(4096, 4096, 3) == 1056817152
+    assert lib.ldc_mask_nnz(5, 5, 1) == 155
+    assert lib.ldc_mask_nnz(2, 4, 3) == -1      # reference: "Crashing" TODO
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("has a GPU")
+    import numpy as np
+    from conftest import synthetic_case
+    from lid_driven_cavity_problem_b200.residual_function import cuda_residual_function as crf
+    g, X = synthetic_case(8, 8)
+    with pytest.raises(RuntimeError):
+        crf.residual_function(X, g)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(REPO, 'lid_driven_cavity_problem_b200')
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.cpp', '.h')):
+                text = open(os.path.join(root, f)).read()
+                assert 'ldc_oracle' not in text and 'from oracle' not in text, os.path.join(root, f)

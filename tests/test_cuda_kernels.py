@@ -1,0 +1,207 @@
+"""GPU parity tests: every CUDA entry point against the CPU oracle and the golden vectors.
+All calls go through the C-ABI (ctypes -> libldc_b200.so)."""
+import numpy as np
+import pytest
+
+from conftest import make_graph, synthetic_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def cuda():
+    import torch
+    from lid_driven_cavity_problem_b200.residual_function import cuda_residual_function as crf
+    from lid_driven_cavity_problem_b200.nonlinear_solver import _common
+    from lid_driven_cavity_problem_b200 import _native
+    return dict(torch=torch, crf=crf, common=_common, native=_native)
+
+
+def _residual_variants(cuda, X, g):
+    torch, crf = cuda['torch'], cuda['crf']
+    Xd = torch.from_numpy(X).cuda()
+    return [crf.residual_function_device(Xd, g, variant=v).cpu().numpy() for v in (1, 2)]
+
+
+def test_reference_3x3_known_answer(cuda, golden):
+    d = golden('residual_3x3_reference_test.npz')
+    from lid_driven_cavity_problem_b200.staggered_grid import Graph
+    g = Graph(1.0, 1.0, 3, 3, 0.01, 1.0, 1.0, 100.0, initial_P=100.0, initial_U=0.001, initial_V=-0.01)
+    F = cuda['crf'].residual_function(d['X'], g)
+    assert isinstance(F, np.ndarray) and F.dtype == np.float64
+    assert np.array_equal(F, d['F'])                 # bit-exact
+    assert np.allclose(F, d['F'], rtol=1e-6, atol=1e-4)  # the reference test's own tolerance
+    for Fv in _residual_variants(cuda, d['X'], g):
+        assert np.array_equal(Fv, d['F'])
+
+
+def test_golden_random_cases_bit_exact(cuda, golden):
+    d = golden('residual_random_cases.npz')
+    for k in range(int(d['count'])):
+        g = make_graph(d['params_%d' % k], 0.9, d['U_%d' % k], d['V_%d' % k], d['P_%d' % k])
+        for tag in ('', '_dummy'):
+            X, F = d['X%s_%d' % (tag, k)], d['F%s_%d' % (tag, k)]
+            for v, Fv in zip((1, 2), _residual_variants(cuda, X, g)):
+                assert np.array_equal(Fv, F), (k, tag, v)
+        # packing
+        common = cuda['common']
+        assert np.array_equal(common._create_X(d['U_%d' % k], d['V_%d' % k], d['P_%d' % k], g), d['X_%d' % k])
+        U, V, P = common._recover_X(d['X_dummy_%d' % k], g)
+        assert np.array_equal(U, d['U_%d' % k]) and np.array_equal(V, d['V_%d' % k])
+        assert np.array_equal(P, d['P_%d' % k])
+
+
+@pytest.mark.parametrize("nx,ny", [(100, 100), (256, 256), (257, 131), (1024, 1024), (61, 1030)])
+def test_residual_vs_oracle(cuda, nx, ny):
+    from oracle import ldc_oracle as orc
+    g, X = synthetic_case(nx, ny)
+    F_ref = orc.residual_function(X, g, nthreads=0)
+    for v, Fv in zip((1, 2), _residual_variants(cuda, X, g)):
+        # north_star: 1e-12 relative (normwise); the kernels are in fact bit-exact
+        assert np.abs(Fv - F_ref).max() <= 1e-12 * np.abs(F_ref).max(), (nx, ny, v)
+        assert np.array_equal(Fv, F_ref), (nx, ny, v)
+    g.use_cds = True
+    F_cds = orc.residual_function(X, g, nthreads=0)
+    for Fv in _residual_variants(cuda, X, g):
+        assert np.array_equal(Fv, F_cds)
+
+
+def test_residual_fused_norm(cuda):
+    torch, crf = cuda['torch'], cuda['crf']
+    for nx, ny in [(100, 100), (513, 300)]:
+        g, X = synthetic_case(nx, ny)
+        Xd = torch.from_numpy(X).cuda()
+        for v in (1, 2):
+            n2 = torch.zeros(1, dtype=torch.float64, device='cuda')
+            F = crf.residual_function_device(Xd, g, variant=v, norm2_out=n2)
+            ref = float(np.dot(F.cpu().numpy(), F.cpu().numpy()))
+            assert abs(n2.item() - ref) <= 1e-12 * ref
+
+
+def test_residual_batch_ensemble(cuda):
+    """Reynolds ensemble: instances back to back, per-instance lid speed on the device."""
+    from oracle import ldc_oracle as orc
+    torch, native = cuda['torch'], cuda['native']
+    nx = ny = 64
+    B = 5
+    bcs = np.array([100.0, 400.0, 1000.0, 3200.0, 10000.0])
+    Xs, Us, Vs, Fs = [], [], [], []
+    for b in range(B):
+        g, X = synthetic_case(nx, ny, bc=bcs[b], seed=b)
+        Xs.append(X); Us.append(g.ns_x_mesh.phi_old); Vs.append(g.ns_y_mesh.phi_old)
+        Fs.append(orc.residual_function(X, g))
+    g, _ = synthetic_case(nx, ny)
+    grid = native.grid_from_graph(g, batch=B)
+    bc_dev = torch.from_numpy(bcs).cuda()
+    grid.bc_dev = bc_dev.data_ptr()
+    Xd = torch.from_numpy(np.concatenate(Xs)).cuda()
+    Ud = torch.from_numpy(np.concatenate(Us)).cuda()
+    Vd = torch.from_numpy(np.concatenate(Vs)).cuda()
+    for v in (1, 2):
+        F = torch.empty_like(Xd)
+        native.check(native.lib().ldc_residual(grid, native.ptr(Xd), native.ptr(Ud), native.ptr(Vd),
+                                               native.ptr(F), None, None, v, native.current_stream()))
+        assert np.array_equal(F.cpu().numpy(), np.concatenate(Fs))
+
+
+def test_residual_row_strips(cuda):
+    """Row-strip decomposition: each strip with its ghost rows reproduces its slice."""
+    from oracle import ldc_oracle as orc
+    torch, native = cuda['torch'], cuda['native']
+    nx, ny = 96, 70
+    g, X = synthetic_case(nx, ny)
+    F_ref = orc.residual_function(X, g)
+    U_old = g.ns_x_mesh.phi_old.reshape(ny, nx - 1)
+    V_old = g.ns_y_mesh.phi_old.reshape(ny - 1, nx)
+    bounds = [0, 17, 18, 40, 70]
+    for v in (1, 2):
+        out = np.empty_like(F_ref)
+        for j0, j1 in zip(bounds[:-1], bounds[1:]):
+            lo, hi = max(j0 - 1, 0), min(j1 + 1, ny)
+            Xl = torch.from_numpy(X[3 * nx * lo:3 * nx * hi].copy()).cuda()
+            Ul = torch.from_numpy(U_old[j0:j1].copy().ravel()).cuda()
+            Vl = torch.from_numpy(V_old[j0:min(j1, ny - 1)].copy().ravel()).cuda()
+            if Vl.numel() == 0:
+                Vl = torch.zeros(1, dtype=torch.float64, device='cuda')
+            Fl = torch.full((3 * nx * (j1 - j0),), np.nan, dtype=torch.float64, device='cuda')
+            grid = native.grid_from_graph(g, row_begin=j0, row_count=j1 - j0)
+            x_ptr = Xl.data_ptr() + 8 * 3 * nx * (j0 - lo)
+            native.check(native.lib().ldc_residual(grid, x_ptr, native.ptr(Ul), native.ptr(Vl), native.ptr(Fl),
+                                                   None, None, v, native.current_stream()))
+            out[3 * nx * j0:3 * nx * j1] = Fl.cpu().numpy()
+        assert np.array_equal(out, F_ref), v
+
+
+def test_mask_bit_exact(cuda, golden):
+    from oracle import ldc_oracle as orc
+    common = cuda['common']
+    d = golden('jacobian_masks.npz')
+    for key in sorted(k[len('indptr_'):] for k in d.files if k.startswith('indptr_')):
+        nx, ny, dof = [int(v) for v in key.split('_')]
+        indptr, indices = common.jacobian_mask_device(nx, ny, dof)
+        assert np.array_equal(indptr.cpu().numpy(), d['indptr_' + key]), key
+        assert np.array_equal(indices.cpu().numpy(), d['indices_' + key]), key
+    for nx, ny in [(100, 100), (256, 256), (64, 64), (1024, 1024)]:
+        indptr, indices = common.jacobian_mask_device(nx, ny, 3)
+        a, b = orc.jacobian_mask_arrays(nx, ny, 3)
+        assert np.array_equal(indptr.cpu().numpy(), a) and np.array_equal(indices.cpu().numpy(), b)
+    m = common._calculate_jacobian_mask(500, 500, 3)   # reference smoke test
+    assert m.nnz == 15732000 and m.has_sorted_indices and m.indices.dtype == np.int32
+    assert np.all(m.data == 1.0)
+
+
+@pytest.mark.parametrize("nx,ny,bc", [(9, 8, 100.0), (13, 9, 400.0), (4, 3, 10.0), (64, 64, 1000.0),
+                                      (100, 100, 1000.0), (131, 77, 3200.0)])
+def test_fd_jacobian_vs_oracle(cuda, nx, ny, bc):
+    from oracle import ldc_oracle as orc
+    torch, native = cuda['torch'], cuda['native']
+    g, X = synthetic_case(nx, ny, bc=bc, seed=7 * nx + ny)
+    # dummy slots carry non-zero values as they do in the middle of a Newton solve
+    X[1::3][nx - 1::nx] = 0.3
+    X[2::3][nx * (ny - 1):] = -0.2
+    mask = orc.jacobian_mask_arrays(nx, ny, 3)
+    J_ref = orc.fd_jacobian(X, g, mask=mask)
+    Xd = torch.from_numpy(X).cuda()
+    Ud = torch.from_numpy(g.ns_x_mesh.phi_old).cuda()
+    Vd = torch.from_numpy(g.ns_y_mesh.phi_old).cuda()
+    vals = torch.full((mask[1].size,), np.nan, dtype=torch.float64, device='cuda')
+    grid = native.grid_from_graph(g)
+    native.check(native.lib().ldc_fd_jacobian(grid, native.ptr(Xd), native.ptr(Ud), native.ptr(Vd),
+                                              native.ptr(vals), native.current_stream()))
+    J = vals.cpu().numpy()
+    assert np.array_equal(J, J_ref)
+
+
+@pytest.mark.parametrize("nx,ny", [(9, 8), (64, 64), (100, 100), (257, 131)])
+def test_spmv_vs_oracle(cuda, nx, ny):
+    from oracle import ldc_oracle as orc
+    torch, native, common = cuda['torch'], cuda['native'], cuda['common']
+    g, X = synthetic_case(nx, ny)
+    mask = orc.jacobian_mask_arrays(nx, ny, 3)
+    J = orc.fd_jacobian(X, g, mask=mask)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(3 * nx * ny)
+    y_ref = orc.spmv(mask, J, x)
+    Jd, xd = torch.from_numpy(J).cuda(), torch.from_numpy(x).cuda()
+    y = torch.empty_like(xd)
+    grid = native.grid_from_graph(g)
+    native.check(native.lib().ldc_spmv_mask(grid, native.ptr(Jd), native.ptr(xd), native.ptr(y),
+                                            native.current_stream()))
+    assert np.array_equal(y.cpu().numpy(), y_ref)
+    indptr, indices = common.jacobian_mask_device(nx, ny, 3)
+    y2 = torch.empty_like(xd)
+    native.check(native.lib().ldc_spmv_csr(3 * nx * ny, native.ptr(indptr), native.ptr(indices), native.ptr(Jd),
+                                           native.ptr(xd), native.ptr(y2), native.current_stream()))
+    assert np.array_equal(y2.cpu().numpy(), y_ref)
+
+
+def test_inputs_are_validated(cuda):
+    crf = cuda['crf']
+    g, X = synthetic_case(16, 16)
+    with pytest.raises(ValueError):
+        crf.residual_function(X[:-1], g)
+    F32 = crf.residual_function(X.astype(np.float32), g)   # converted, not reinterpreted
+    assert F32.dtype == np.float64 and F32.shape == X.shape
+    X0 = X.copy()
+    crf.residual_function(X, g)
+    assert np.array_equal(X, X0)                            # pure
