@@ -103,17 +103,21 @@ typedef struct ldc_solver ldc_solver;
 
 typedef struct ldc_solver_options {
     double snes_rtol, snes_atol, snes_stol;   /* 1e-4 each  (petsc_solver_wrapper.py:135) */
+    double snes_divtol;                       /* 1e4: ||F|| > divtol*||F0|| -> reason -9 (PETSc default) */
     int32_t snes_max_it;                      /* 50 */
     int32_t snes_max_funcs;                   /* 10000 (PETSc default) */
     double ksp_rtol, ksp_atol, ksp_dtol;      /* 1e-5, 1e-50, 1e5 (PETSc KSP defaults) */
-    int32_t ksp_max_it;                       /* 10000 */
+    int32_t ksp_max_it;                       /* 500 (PETSc: 10000 with ILU) */
     int32_t gmres_restart;                    /* 30 */
     int32_t pc_type;                          /* LDC_PC_* */
-    int32_t pc_sweeps;                        /* smoothing sweeps per level / per application */
+    int32_t pc_sweeps;                        /* relaxation sweeps before and after each coarse correction */
     int32_t mg_levels;                        /* 0 = auto (coarsen while both sizes are even) */
-    double pc_omega_u, pc_omega_p;            /* damping of the cell-block relaxation */
+    int32_t mg_coarse_sweeps;                 /* relaxation sweeps on the coarsest grid */
+    int32_t mg_min_size;                      /* do not coarsen below this many cells per side */
     int32_t residual_variant;                 /* as in ldc_residual */
+    int32_t gmres_refine;                     /* 1: second Gram-Schmidt pass (CGS2); 0: PETSc's default (never) */
     int32_t reserved;
+    double pc_omega_u, pc_omega_p;            /* damping of the cell-block relaxation */
 } ldc_solver_options;
 
 #define LDC_PC_NONE 0
@@ -140,6 +144,19 @@ LDC_API void ldc_solver_destroy(ldc_solver *s);
 LDC_API double *ldc_solver_state_dev(ldc_solver *s);
 /* set per-instance dt (host array of `batch` doubles) */
 LDC_API int ldc_solver_set_dt(ldc_solver *s, const double *dt_host);
+/* set per-instance lid speed (host array of `batch` doubles) */
+LDC_API int ldc_solver_set_bc(ldc_solver *s, const double *bc_host);
+/* device-to-device copies of the whole interleaved state */
+LDC_API int ldc_solver_set_state(ldc_solver *s, const double *X_dev, void *stream);
+LDC_API int ldc_solver_get_state(ldc_solver *s, double *X_dev, void *stream);
+/* number of multigrid levels the solver built */
+LDC_API int ldc_solver_num_levels(ldc_solver *s);
+/* Building block exposed for the parity tests: assemble the FD Jacobian (and its multigrid
+ * hierarchy) at the current state and solve J y = rhs with the preconditioned GMRES.
+ * Host outputs are per instance.  Synchronises the stream. */
+LDC_API int ldc_solver_linear_solve(ldc_solver *s, const double *rhs_dev, double *y_dev,
+                                    int32_t *its_host, int32_t *reason_host, double *relres_host,
+                                    void *stream);
 /* One pseudo-time step for every ACTIVE instance: X_old <- X, Newton solve, X <- solution.
  * active_host[batch] (NULL = all) selects instances; diverged instances keep X = X_old.
  * reports_host[batch] is filled.  Synchronises the stream before returning.

@@ -26,14 +26,16 @@ class LdcGrid(ctypes.Structure):
 
 class LdcSolverOptions(ctypes.Structure):
     _fields_ = [('snes_rtol', ctypes.c_double), ('snes_atol', ctypes.c_double),
-                ('snes_stol', ctypes.c_double), ('snes_max_it', ctypes.c_int32),
-                ('snes_max_funcs', ctypes.c_int32), ('ksp_rtol', ctypes.c_double),
-                ('ksp_atol', ctypes.c_double), ('ksp_dtol', ctypes.c_double),
+                ('snes_stol', ctypes.c_double), ('snes_divtol', ctypes.c_double),
+                ('snes_max_it', ctypes.c_int32), ('snes_max_funcs', ctypes.c_int32),
+                ('ksp_rtol', ctypes.c_double), ('ksp_atol', ctypes.c_double),
+                ('ksp_dtol', ctypes.c_double),
                 ('ksp_max_it', ctypes.c_int32), ('gmres_restart', ctypes.c_int32),
                 ('pc_type', ctypes.c_int32), ('pc_sweeps', ctypes.c_int32),
                 ('mg_levels', ctypes.c_int32), ('mg_coarse_sweeps', ctypes.c_int32),
-                ('pc_omega_u', ctypes.c_double), ('pc_omega_p', ctypes.c_double),
-                ('residual_variant', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+                ('mg_min_size', ctypes.c_int32), ('residual_variant', ctypes.c_int32),
+                ('gmres_refine', ctypes.c_int32), ('reserved', ctypes.c_int32),
+                ('pc_omega_u', ctypes.c_double), ('pc_omega_p', ctypes.c_double)]
 
 
 class LdcNewtonReport(ctypes.Structure):
@@ -63,13 +65,16 @@ SYMBOLS = {
     'ldc_fd_jacobian': (ctypes.c_int, [_grid_p, _vp, _vp, _vp, _vp, _vp]),
     'ldc_spmv_mask': (ctypes.c_int, [_grid_p, _vp, _vp, _vp, _vp]),
     'ldc_spmv_csr': (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
-}
-SOLVER_SYMBOLS = {
     'ldc_solver_default_options': (None, [ctypes.POINTER(LdcSolverOptions)]),
     'ldc_solver_create': (ctypes.c_int, [_grid_p, ctypes.POINTER(LdcSolverOptions), ctypes.POINTER(_vp)]),
     'ldc_solver_destroy': (None, [_vp]),
     'ldc_solver_state_dev': (_vp, [_vp]),
     'ldc_solver_set_dt': (ctypes.c_int, [_vp, c_double_p]),
+    'ldc_solver_set_bc': (ctypes.c_int, [_vp, c_double_p]),
+    'ldc_solver_set_state': (ctypes.c_int, [_vp, _vp, _vp]),
+    'ldc_solver_get_state': (ctypes.c_int, [_vp, _vp, _vp]),
+    'ldc_solver_num_levels': (ctypes.c_int, [_vp]),
+    'ldc_solver_linear_solve': (ctypes.c_int, [_vp, _vp, _vp, c_int32_p, c_int32_p, c_double_p, _vp]),
     'ldc_solver_step': (ctypes.c_int, [_vp, c_int32_p, ctypes.POINTER(LdcNewtonReport), c_double_p, _vp]),
 }
 

@@ -1,0 +1,336 @@
+// Preconditioner of the Krylov solve (sm_100a): additive cell-block relaxation and the
+// transfer operators of a geometric multigrid hierarchy on the staggered grid.
+//
+// Role in the reference: PETSc's PC (pc_type ilu with pc_factor_shift_type NONZERO,
+// petsc_solver_wrapper.py:141-143).  ILU(0) in natural ordering is a sequential wavefront
+// algorithm and its Krylov iteration count grows ~3x per grid doubling on this saddle-point
+// system (oracle probe: 30/100/300 at 32^2/64^2/128^2).  The B200 design replaces it by
+//   * a cell-block ("Vanka") relaxation: every pressure cell solves the 5x5 system that
+//     couples its pressure with its (up to) four face velocities, momentum rows reduced to
+//     their diagonal; all cells are relaxed at once from the same residual (additive /
+//     block-Jacobi form, two cells share each face -> weight 1/2), so a sweep is one SpMV plus
+//     two streaming passes, fully parallel and deterministic;
+//   * a multigrid V-cycle over grids nx/2^l x ny/2^l whose operators are the SAME coloured-FD
+//     Jacobian kernel evaluated on the restricted state (finite-volume residuals are integrals,
+//     so summing fine residuals and interpolating corrections needs no rescaling).
+// Only the converged state has to agree with the reference; iteration counts differ by design.
+#include "solver_internal.cuh"
+
+namespace ldc {
+
+// ---------------------------------------------------------------------------------------------
+// state restriction: P = mean of the 4 children, U/V = mean of the two fine faces lying on the
+// coarse face; coarse dummy slots = 0.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+restrict_state_kernel(int nxf, int nyf, const double *__restrict__ Xf, double *__restrict__ Xc)
+{
+    const int nxc = nxf / 2, nyc = nyf / 2;
+    const long Nc = (long)nxc * nyc;
+    const long c = (long)blockIdx.x * 256 + threadIdx.x;
+    if (c >= Nc) return;
+    const int b = blockIdx.y;
+    Xf += (long)b * 3 * nxf * nyf;
+    Xc += (long)b * 3 * Nc;
+    const int J = (int)(c / nxc), I = (int)(c - (long)J * nxc);
+    auto f = [&](int i, int j, int d) { return Xf[3 * ((long)i + (long)nxf * j) + d]; };
+    const int i0 = 2 * I, j0 = 2 * J;
+    Xc[3 * c] = 0.25 * (f(i0, j0, 0) + f(i0 + 1, j0, 0) + f(i0, j0 + 1, 0) + f(i0 + 1, j0 + 1, 0));
+    Xc[3 * c + 1] = (I < nxc - 1) ? 0.5 * (f(i0 + 1, j0, 1) + f(i0 + 1, j0 + 1, 1)) : 0.0;
+    Xc[3 * c + 2] = (J < nyc - 1) ? 0.5 * (f(i0, j0 + 1, 2) + f(i0 + 1, j0 + 1, 2)) : 0.0;
+}
+
+__global__ void __launch_bounds__(256)
+extract_diag_kernel(int nx, int ny, long nnz, const double *__restrict__ J, double *__restrict__ diag)
+{
+    const long N = (long)nx * ny;
+    const long r = (long)blockIdx.x * 256 + threadIdx.x;
+    if (r >= 3 * N) return;
+    const int b = blockIdx.y;
+    const MaskGeom m{nx, N};
+    const long c = r / 3;
+    const int d = (int)(r - 3 * c);
+    diag[(long)b * 3 * N + r] = J[(long)b * nnz + m.row_start(c, d) + 3 * (3 - m.lo_missing(c)) + d];
+}
+
+// ---------------------------------------------------------------------------------------------
+// cell-block relaxation.  Local system of cell c=(i,j) with the analytic pressure/divergence
+// couplings of the discretisation (residual_function.cpp:77-84,151: dC/dU_e=+dy, dC/dU_w=-dy,
+// dC/dV_n=+dx, dC/dV_s=-dx; dFu(c)/dP(c)=-dy, dFu(c-1)/dP(c)=+dy, dFv(c)/dP(c)=-dx,
+// dFv(c-nx)/dP(c)=+dx) and the momentum diagonals a_* taken from the FD Jacobian:
+//     a_k du_k + g_k dp = r_k  (k = w,e,s,n)      sum_k d_k du_k = r_c
+//  => dp = (sum_k d_k r_k / a_k - r_c) / (sum_k d_k g_k / a_k),   du_k = (r_k - g_k dp) / a_k
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+vanka_dp_kernel(int nx, int ny, double dx, double dy, const double *__restrict__ r,
+                const double *__restrict__ diag, double *__restrict__ dp,
+                const int32_t *__restrict__ run)
+{
+    const int b = blockIdx.y;
+    if (run && !run[b]) return;
+    const long N = (long)nx * ny;
+    const long c = (long)blockIdx.x * 256 + threadIdx.x;
+    if (c >= N) return;
+    r += (long)b * 3 * N;
+    diag += (long)b * 3 * N;
+    const int j = (int)(c / nx), i = (int)(c - (long)j * nx);
+    double num = -r[3 * c];
+    double den = 0.0;
+    if (i < nx - 1) {  // east face: U row of cell c, d=+dy, g=-dy
+        const double ia = 1.0 / diag[3 * c + 1];
+        num += dy * r[3 * c + 1] * ia;
+        den -= dy * dy * ia;
+    }
+    if (i > 0) {       // west face: U row of cell c-1, d=-dy, g=+dy
+        const double ia = 1.0 / diag[3 * (c - 1) + 1];
+        num -= dy * r[3 * (c - 1) + 1] * ia;
+        den -= dy * dy * ia;
+    }
+    if (j < ny - 1) {  // north face: V row of cell c, d=+dx, g=-dx
+        const double ia = 1.0 / diag[3 * c + 2];
+        num += dx * r[3 * c + 2] * ia;
+        den -= dx * dx * ia;
+    }
+    if (j > 0) {       // south face: V row of cell c-nx, d=-dx, g=+dx
+        const double ia = 1.0 / diag[3 * (c - nx) + 2];
+        num -= dx * r[3 * (c - nx) + 2] * ia;
+        den -= dx * dx * ia;
+    }
+    dp[(long)b * N + c] = (den != 0.0) ? num / den : 0.0;
+}
+
+// x (+)= omega * correction ; ASSIGN: x is taken as zero before the sweep
+template <bool ASSIGN>
+__global__ void __launch_bounds__(256)
+vanka_update_kernel(int nx, int ny, double dx, double dy, double om_u, double om_p,
+                    const double *__restrict__ r, const double *__restrict__ diag,
+                    const double *__restrict__ dp, double *__restrict__ x,
+                    const int32_t *__restrict__ run)
+{
+    const int b = blockIdx.y;
+    if (run && !run[b]) return;
+    const long N = (long)nx * ny;
+    const long c = (long)blockIdx.x * 256 + threadIdx.x;
+    if (c >= N) return;
+    r += (long)b * 3 * N;
+    diag += (long)b * 3 * N;
+    dp += (long)b * N;
+    x += (long)b * 3 * N;
+    const int j = (int)(c / nx), i = (int)(c - (long)j * nx);
+    const double p_c = dp[c];
+    double e0 = om_p * p_c, e1, e2;
+    if (i < nx - 1) {
+        // face shared by cells c (as east face, g=-dy) and c+1 (as west face, g=+dy)
+        const double ru = r[3 * c + 1];
+        e1 = 0.5 * om_u * ((ru + dy * p_c) + (ru - dy * dp[c + 1])) / diag[3 * c + 1];
+    } else {
+        e1 = r[3 * c + 1] / diag[3 * c + 1];  // dummy row (identity)
+    }
+    if (j < ny - 1) {
+        const double rv = r[3 * c + 2];
+        e2 = 0.5 * om_u * ((rv + dx * p_c) + (rv - dx * dp[c + nx])) / diag[3 * c + 2];
+    } else {
+        e2 = r[3 * c + 2] / diag[3 * c + 2];
+    }
+    if (ASSIGN) {
+        x[3 * c] = e0;
+        x[3 * c + 1] = e1;
+        x[3 * c + 2] = e2;
+    } else {
+        x[3 * c] += e0;
+        x[3 * c + 1] += e1;
+        x[3 * c + 2] += e2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// residual restriction (sum over the fine control volumes covered by the coarse one):
+//   continuity: the 4 children;  U rows: weights [1/2,1,1/2] over fine faces 2I,2I+1,2I+2 and
+//   both fine rows;  V rows: transposed.  Coarse dummy rows get 0.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+restrict_residual_kernel(int nxf, int nyf, const double *__restrict__ rf, double *__restrict__ bc,
+                         const int32_t *__restrict__ run)
+{
+    const int b = blockIdx.y;
+    if (run && !run[b]) return;
+    const int nxc = nxf / 2, nyc = nyf / 2;
+    const long Nc = (long)nxc * nyc;
+    const long c = (long)blockIdx.x * 256 + threadIdx.x;
+    if (c >= Nc) return;
+    rf += (long)b * 3 * nxf * nyf;
+    bc += (long)b * 3 * Nc;
+    const int J = (int)(c / nxc), I = (int)(c - (long)J * nxc);
+    auto f = [&](int i, int j, int d) { return rf[3 * ((long)i + (long)nxf * j) + d]; };
+    const int i0 = 2 * I, j0 = 2 * J;
+    bc[3 * c] = (f(i0, j0, 0) + f(i0 + 1, j0, 0)) + (f(i0, j0 + 1, 0) + f(i0 + 1, j0 + 1, 0));
+    double u = 0.0, v = 0.0;
+    if (I < nxc - 1) {
+        u = 0.5 * (f(i0, j0, 1) + f(i0, j0 + 1, 1)) + (f(i0 + 1, j0, 1) + f(i0 + 1, j0 + 1, 1)) +
+            0.5 * (f(i0 + 2, j0, 1) + f(i0 + 2, j0 + 1, 1));
+    }
+    if (J < nyc - 1) {
+        v = 0.5 * (f(i0, j0, 2) + f(i0 + 1, j0, 2)) + (f(i0, j0 + 1, 2) + f(i0 + 1, j0 + 1, 2)) +
+            0.5 * (f(i0, j0 + 2, 2) + f(i0 + 1, j0 + 2, 2));
+    }
+    bc[3 * c + 1] = u;
+    bc[3 * c + 2] = v;
+}
+
+// prolongation = transpose of the restriction above, added to the fine correction
+__global__ void __launch_bounds__(256)
+prolong_add_kernel(int nxf, int nyf, const double *__restrict__ xc, double *__restrict__ xf,
+                   const int32_t *__restrict__ run)
+{
+    const int b = blockIdx.y;
+    if (run && !run[b]) return;
+    const int nxc = nxf / 2, nyc = nyf / 2;
+    const long Nf = (long)nxf * nyf;
+    const long c = (long)blockIdx.x * 256 + threadIdx.x;
+    if (c >= Nf) return;
+    xc += (long)b * 3 * nxc * nyc;
+    xf += (long)b * 3 * Nf;
+    const int j = (int)(c / nxf), i = (int)(c - (long)j * nxf);
+    const int I = i >> 1, J = j >> 1;
+    auto g = [&](int II, int JJ, int d) { return xc[3 * ((long)II + (long)nxc * JJ) + d]; };
+    xf[3 * c] += g(I, J, 0);
+    if (i < nxf - 1) {
+        double u;
+        if (i & 1) u = g(I, J, 1);  // fine face on the coarse face (I <= nxc-2 here)
+        else u = 0.5 * ((I >= 1 ? g(I - 1, J, 1) : 0.0) + (I < nxc - 1 ? g(I, J, 1) : 0.0));
+        xf[3 * c + 1] += u;
+    }
+    if (j < nyf - 1) {
+        double v;
+        if (j & 1) v = g(I, J, 2);
+        else v = 0.5 * ((J >= 1 ? g(I, J - 1, 2) : 0.0) + (J < nyc - 1 ? g(I, J, 2) : 0.0));
+        xf[3 * c + 2] += v;
+    }
+}
+
+// x_P -= mean(x_P): removes the constant-pressure mode (the Jacobian's null space)
+// from a coarse-grid correction.  One block per instance; meant for the small coarsest grid.
+__global__ void __launch_bounds__(256)
+remove_mean_pressure_kernel(long N, double *__restrict__ x, const int32_t *__restrict__ run)
+{
+    const int b = blockIdx.x;
+    if (run && !run[b]) return;
+    x += (long)b * 3 * N;
+    __shared__ double sm[256];
+    double s = 0.0;
+    for (long c = threadIdx.x; c < N; c += 256) s += x[3 * c];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+        __syncthreads();
+    }
+    const double mean = sm[0] / (double)N;
+    for (long c = threadIdx.x; c < N; c += 256) x[3 * c] -= mean;
+}
+
+// large grids: chunked partial sums of the pressure slots, fixed-order reduction, subtraction
+__global__ void __launch_bounds__(256)
+pressure_sum_partials_kernel(long N, const double *__restrict__ x, double *__restrict__ partials,
+                             const int32_t *__restrict__ run)
+{
+    const int b = blockIdx.y;
+    if (run && !run[b]) return;
+    x += (long)b * 3 * N;
+    const long c0 = (long)blockIdx.x * 2048;
+    double s = 0.0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const long c = c0 + threadIdx.x + (long)e * 256;
+        if (c < N) s += x[3 * c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ double sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += sm[k];
+        partials[(long)b * gridDim.x + blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+subtract_mean_pressure_kernel(long N, double *__restrict__ x, const double *__restrict__ sums,
+                              const int32_t *__restrict__ run)
+{
+    const int b = blockIdx.y;
+    if (run && !run[b]) return;
+    const long c = (long)blockIdx.x * 256 + threadIdx.x;
+    if (c < N) x[(long)b * 3 * N + 3 * c] -= sums[b] / (double)N;
+}
+
+int mg_remove_mean_pressure(const MgLevel &l, double *x, int batch, const int32_t *run,
+                            double *partials, double *sums, cudaStream_t s)
+{
+    if (l.N <= 4096 || partials == nullptr) {
+        remove_mean_pressure_kernel<<<batch, 256, 0, s>>>(l.N, x, run);
+        LDC_CHECK_LAUNCH();
+        return LDC_OK;
+    }
+    const int nblk = (int)((l.N + 2047) / 2048);
+    pressure_sum_partials_kernel<<<dim3(nblk, batch), 256, 0, s>>>(l.N, x, partials, run);
+    LDC_CHECK_LAUNCH();
+    if (int rc = vec_reduce_partials(partials, 1, nblk, batch, sums, s)) return rc;
+    subtract_mean_pressure_kernel<<<dim3((unsigned)((l.N + 255) / 256), batch), 256, 0, s>>>(l.N, x, sums, run);
+    LDC_CHECK_LAUNCH();
+    return LDC_OK;
+}
+
+static dim3 cell_grid(long N, int batch) { return dim3((unsigned)((N + 255) / 256), batch); }
+
+int mg_restrict_state(const MgLevel &f, const MgLevel &c, int batch, cudaStream_t s)
+{
+    restrict_state_kernel<<<cell_grid(c.N, batch), 256, 0, s>>>(f.nx, f.ny, f.X, c.X);
+    LDC_CHECK_LAUNCH();
+    return LDC_OK;
+}
+
+int mg_extract_diag(const MgLevel &l, int batch, cudaStream_t s)
+{
+    extract_diag_kernel<<<cell_grid(l.n, batch), 256, 0, s>>>(l.nx, l.ny, l.nnz, l.J, l.diag);
+    LDC_CHECK_LAUNCH();
+    return LDC_OK;
+}
+
+int mg_vanka_sweep(const MgLevel &l, const double *b, double *x, bool zero_guess, double om_u,
+                   double om_p, int batch, const int32_t *run, cudaStream_t s)
+{
+    const double *r = b;
+    if (!zero_guess) {
+        if (int rc = spmv_mask_launch(l.nx, l.ny, batch, l.J, x, b, l.r, run, s)) return rc;
+        r = l.r;
+    }
+    vanka_dp_kernel<<<cell_grid(l.N, batch), 256, 0, s>>>(l.nx, l.ny, l.dx, l.dy, r, l.diag, l.dp, run);
+    LDC_CHECK_LAUNCH();
+    if (zero_guess)
+        vanka_update_kernel<true><<<cell_grid(l.N, batch), 256, 0, s>>>(l.nx, l.ny, l.dx, l.dy, om_u, om_p, r, l.diag, l.dp, x, run);
+    else
+        vanka_update_kernel<false><<<cell_grid(l.N, batch), 256, 0, s>>>(l.nx, l.ny, l.dx, l.dy, om_u, om_p, r, l.diag, l.dp, x, run);
+    LDC_CHECK_LAUNCH();
+    return LDC_OK;
+}
+
+int mg_restrict_residual(const MgLevel &f, const double *r_f, const MgLevel &c, double *b_c,
+                         int batch, const int32_t *run, cudaStream_t s)
+{
+    restrict_residual_kernel<<<cell_grid(c.N, batch), 256, 0, s>>>(f.nx, f.ny, r_f, b_c, run);
+    LDC_CHECK_LAUNCH();
+    return LDC_OK;
+}
+
+int mg_prolong_add(const MgLevel &c, const double *x_c, const MgLevel &f, double *x_f, int batch,
+                   const int32_t *run, cudaStream_t s)
+{
+    prolong_add_kernel<<<cell_grid(f.N, batch), 256, 0, s>>>(f.nx, f.ny, x_c, x_f, run);
+    LDC_CHECK_LAUNCH();
+    return LDC_OK;
+}
+
+}  // namespace ldc

@@ -1,0 +1,679 @@
+// Device-resident Newton-Krylov solve of one pseudo-time step (sm_100a).
+//
+// Replaces PetscSolverWrapper.solve / _setup_snes / _setup_options
+// (nonlinear_solver/petsc_solver_wrapper.py:35-145), i.e. PETSc's SNES newtonls with line
+// search 'basic' (full steps), Jacobian by coloured finite differences, KSP GMRES(30):
+//   * state, residual, Jacobian values, Krylov basis and the multigrid hierarchy live in HBM
+//     for the whole run; per Newton iteration the host reads back three norms per cavity,
+//     per Krylov iteration one residual estimate per cavity (a few bytes);
+//   * mask / colouring / workspace are built once per solver (the reference rebuilds its SNES,
+//     mask and colouring every time step because `_first_run` is never cleared,
+//     petsc_solver_wrapper.py:39,71-72);
+//   * Newton tolerances, reason codes and the order of the convergence tests follow
+//     SNESConvergedDefault (rtol=atol=stol=1e-4, max_it=50, petsc_solver_wrapper.py:135);
+//   * the linear solve is restarted flexible GMRES, right-preconditioned by the multigrid
+//     V-cycle of precond.cu, converged on the TRUE residual ||F - J y|| <= max(rtol*||F||, atol)
+//     (PETSc's default is left preconditioning on the preconditioned residual; only the
+//     converged state has to agree with the reference).
+// A batch of independent cavities (Reynolds ensemble) advances in lock step; finished cavities
+// are masked out on the device.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "solver_internal.cuh"
+
+namespace ldc {
+
+// per-instance GMRES scalars on the device
+struct KrylovSmall {
+    double *H;      // [batch][(m+1)*m] column major
+    double *cs, *sn;  // [batch][m]
+    double *gv;     // [batch][m+1]
+    double *yv;     // [batch][m]
+    double *hcol;   // [batch][k+1] packed: dots of the current column against v_0..v_k
+    double *nrm2;   // [batch]        scratch for reduced squared norms
+    double *beta;   // [batch]        residual norm at cycle start
+    double *res;    // [batch]        current residual estimate
+    double *hnext;  // [batch]        h_{k+1,k} before rotation
+    double *hcol2;  // [batch][k+1] packed: second (re-orthogonalisation) pass
+};
+
+// h += h2 (packed columns of all instances)
+__global__ void add_columns_kernel(double *h, const double *h2, int total)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < total) h[t] += h2[t];
+}
+
+__global__ void krylov_begin_cycle_kernel(KrylovSmall ks, int m, int batch, const int32_t *run)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    if (run && !run[b]) return;
+    double *gv = ks.gv + (long)b * (m + 1);
+    for (int i = 0; i <= m; ++i) gv[i] = 0.0;
+    gv[0] = ks.beta[b];
+    ks.res[b] = ks.beta[b];
+}
+
+// sqrt of a reduced squared norm (per instance)
+__global__ void sqrt_kernel(const double *in, double *out, int batch, const int32_t *run)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    if (run && !run[b]) return;
+    out[b] = sqrt(in[b]);
+}
+
+// column k: store h, apply the stored Givens rotations, create the new one, update g
+__global__ void krylov_givens_kernel(KrylovSmall ks, int m, int k, int batch, const int32_t *run)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    if (run && !run[b]) return;
+    double *H = ks.H + (long)b * (m + 1) * m + (long)k * (m + 1);
+    double *cs = ks.cs + (long)b * m, *sn = ks.sn + (long)b * m;
+    double *gv = ks.gv + (long)b * (m + 1);
+    const double *h = ks.hcol + (long)b * (k + 1);  // packed [batch][k+1] by vec_reduce_partials
+    const double hk1 = sqrt(ks.nrm2[b]);
+    ks.hnext[b] = hk1;
+    for (int i = 0; i <= k; ++i) H[i] = h[i];
+    H[k + 1] = hk1;
+    for (int i = 0; i < k; ++i) {
+        const double a = H[i], c = H[i + 1];
+        H[i] = cs[i] * a + sn[i] * c;
+        H[i + 1] = -sn[i] * a + cs[i] * c;
+    }
+    const double a = H[k], c = H[k + 1];
+    const double d = sqrt(a * a + c * c);
+    if (d == 0.0) { cs[k] = 1.0; sn[k] = 0.0; }
+    else { cs[k] = a / d; sn[k] = c / d; }
+    H[k] = cs[k] * a + sn[k] * c;
+    H[k + 1] = 0.0;
+    gv[k + 1] = -sn[k] * gv[k];
+    gv[k] = cs[k] * gv[k];
+    ks.res[b] = fabs(gv[k + 1]);
+}
+
+// back substitution H(0:kk,0:kk) y = g(0:kk)
+__global__ void krylov_solve_y_kernel(KrylovSmall ks, int m, int kk, int batch, const int32_t *run)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    if (run && !run[b]) return;
+    const double *H = ks.H + (long)b * (m + 1) * m;
+    const double *gv = ks.gv + (long)b * (m + 1);
+    double *y = ks.yv + (long)b * m;
+    for (int i = kk - 1; i >= 0; --i) {
+        double s = gv[i];
+        for (int j = i + 1; j < kk; ++j) s -= H[(long)j * (m + 1) + i] * y[j];
+        const double d = H[(long)i * (m + 1) + i];
+        y[i] = (d != 0.0) ? s / d : 0.0;
+    }
+}
+
+// U_old, V_old <- the velocity slots of X (masked per instance)
+__global__ void __launch_bounds__(256)
+extract_old_kernel(int nx, int ny, const double *__restrict__ X, double *__restrict__ U_old,
+                   double *__restrict__ V_old, const int32_t *__restrict__ run)
+{
+    const int b = blockIdx.y;
+    if (run && !run[b]) return;
+    const long N = (long)nx * ny;
+    const long c = (long)blockIdx.x * 256 + threadIdx.x;
+    if (c >= N) return;
+    const int j = (int)(c / nx), i = (int)(c - (long)j * nx);
+    const double *x = X + 3 * ((long)b * N + c);
+    if (i < nx - 1) U_old[(long)b * (nx - 1) * ny + i + (long)(nx - 1) * j] = x[1];
+    if (j < ny - 1) V_old[(long)b * nx * (ny - 1) + c] = x[2];
+}
+
+}  // namespace ldc
+
+using namespace ldc;
+
+struct ldc_solver {
+    ldc_grid g;
+    ldc_solver_options opt;
+    int batch, m;
+    long N, n, nnz;
+    std::vector<void *> dev_allocs, host_allocs;
+    // state
+    double *X, *X_prev, *F, *Y, *U_old, *V_old;
+    double *dt_dev, *bc_dev;
+    std::vector<MgLevel> levels;
+    // Krylov
+    double *V, *Z, *w, *rres;
+    double *partials, *res_work;
+    long partial_doubles;
+    KrylovSmall ks;
+    int32_t *run_dev, *fin_dev;
+    double *scal_dev;   // [3*batch] fnorm2, ynorm2, xnorm2
+    // pinned host mirrors
+    double *scal_host, *res_host, *du_host;
+    int32_t *mask_host;
+    std::vector<double> dt_host, bc_host;
+    long total_linear_its;
+
+    template <typename T>
+    int dalloc(T **p, size_t count)
+    {
+        void *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 256);
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+            return LDC_ERR_ALLOC;
+        }
+        dev_allocs.push_back(q);
+        *p = (T *)q;
+        return LDC_OK;
+    }
+    template <typename T>
+    int halloc(T **p, size_t count)
+    {
+        void *q = nullptr;
+        cudaError_t e = cudaMallocHost(&q, count * sizeof(T) + 64);
+        if (e != cudaSuccess) {
+            set_error("cudaMallocHost failed: %s", cudaGetErrorString(e));
+            return LDC_ERR_ALLOC;
+        }
+        host_allocs.push_back(q);
+        *p = (T *)q;
+        return LDC_OK;
+    }
+};
+
+#define TRY(expr)                    \
+    do {                             \
+        int rc__ = (expr);           \
+        if (rc__ != LDC_OK) return rc__; \
+    } while (0)
+
+extern "C" void ldc_solver_default_options(ldc_solver_options *o)
+{
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->snes_rtol = o->snes_atol = o->snes_stol = 1e-4;  // petsc_solver_wrapper.py:135
+    o->snes_max_it = 50;
+    o->snes_max_funcs = 10000;
+    o->snes_divtol = 1e4;   // PETSc -snes_divergence_tolerance default
+    o->ksp_rtol = 1e-5;     // PETSc KSP defaults
+    o->ksp_atol = 1e-50;
+    o->ksp_dtol = 1e5;
+    o->ksp_max_it = 500;    // PETSc: 10000 (ILU); a multigrid-preconditioned solve that needs more has failed
+    o->gmres_restart = 30;
+    o->gmres_refine = 1;
+    o->pc_type = LDC_PC_MG_VANKA;
+    o->pc_sweeps = 2;
+    o->mg_levels = 0;
+    o->mg_coarse_sweeps = 30;
+    o->mg_min_size = 4;
+    o->pc_omega_u = 0.7;
+    o->pc_omega_p = 0.7;
+    o->residual_variant = 0;
+}
+
+static ldc_grid level_grid(const ldc_solver *s, const MgLevel &l)
+{
+    ldc_grid g = s->g;
+    g.nx = l.nx;
+    g.ny = l.ny;
+    g.row_begin = 0;
+    g.row_count = l.ny;
+    g.dx = l.dx;
+    g.dy = l.dy;
+    g.dt_dev = s->dt_dev;
+    g.bc_dev = s->bc_dev;
+    return g;
+}
+
+extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *opt, ldc_solver **out)
+{
+    LDC_REQUIRE(out != nullptr, "ldc_solver_create: out is NULL");
+    *out = nullptr;
+    TRY(validate_grid(g, true));
+    ldc_solver_options o;
+    if (opt) o = *opt; else ldc_solver_default_options(&o);
+    LDC_REQUIRE(o.gmres_restart >= 1 && o.gmres_restart <= kMaxRestart, "gmres_restart must be in [1,%d]", kMaxRestart);
+    LDC_REQUIRE(o.pc_type >= LDC_PC_NONE && o.pc_type <= LDC_PC_MG_VANKA, "unknown pc_type %d", o.pc_type);
+    LDC_REQUIRE(o.pc_sweeps >= 1 && o.mg_coarse_sweeps >= 1, "sweep counts must be >= 1");
+    ldc_solver *s = new ldc_solver();
+    s->g = *g;
+    s->opt = o;
+    s->batch = g->batch;
+    s->m = o.gmres_restart;
+    s->N = (long)g->nx * g->ny;
+    s->n = 3 * s->N;
+    s->nnz = ldc_mask_nnz(g->nx, g->ny, 3);
+    s->total_linear_its = 0;
+    const int B = s->batch, m = s->m;
+    const long n = s->n;
+    int rc = LDC_OK;
+#define A(expr) do { if (rc == LDC_OK) rc = (expr); } while (0)
+    A(s->dalloc(&s->X, (size_t)B * n));
+    A(s->dalloc(&s->X_prev, (size_t)B * n));
+    A(s->dalloc(&s->F, (size_t)B * n));
+    A(s->dalloc(&s->Y, (size_t)B * n));
+    A(s->dalloc(&s->U_old, (size_t)B * (g->nx - 1) * g->ny));
+    A(s->dalloc(&s->V_old, (size_t)B * g->nx * (g->ny - 1)));
+    A(s->dalloc(&s->dt_dev, B));
+    A(s->dalloc(&s->bc_dev, B));
+    // multigrid hierarchy
+    int nlev = 1;
+    if (o.pc_type == LDC_PC_MG_VANKA) {
+        int nx = g->nx, ny = g->ny;
+        const int min_size = o.mg_min_size > 2 ? o.mg_min_size : 3;
+        while (nx % 2 == 0 && ny % 2 == 0 && nx / 2 >= min_size && ny / 2 >= min_size &&
+               (o.mg_levels <= 0 || nlev < o.mg_levels)) {
+            nx /= 2; ny /= 2; ++nlev;
+        }
+    }
+    s->levels.resize(nlev);
+    for (int l = 0; l < nlev && rc == LDC_OK; ++l) {
+        MgLevel &L = s->levels[l];
+        L.nx = g->nx >> l;
+        L.ny = g->ny >> l;
+        L.dx = g->dx * (double)(1 << l);
+        L.dy = g->dy * (double)(1 << l);
+        L.N = (long)L.nx * L.ny;
+        L.n = 3 * L.N;
+        L.nnz = ldc_mask_nnz(L.nx, L.ny, 3);
+        L.X = nullptr; L.x = L.b = nullptr;
+        if (l == 0) L.X = s->X;
+        else {
+            A(s->dalloc(&L.X, (size_t)B * L.n));
+            A(s->dalloc(&L.x, (size_t)B * L.n));
+            A(s->dalloc(&L.b, (size_t)B * L.n));
+        }
+        A(s->dalloc(&L.J, (size_t)B * L.nnz));
+        A(s->dalloc(&L.diag, (size_t)B * L.n));
+        A(s->dalloc(&L.r, (size_t)B * L.n));
+        A(s->dalloc(&L.dp, (size_t)B * L.N));
+    }
+    // Krylov workspace
+    A(s->dalloc(&s->V, (size_t)(m + 1) * B * n));
+    A(s->dalloc(&s->Z, (size_t)m * B * n));
+    A(s->dalloc(&s->w, (size_t)B * n));
+    A(s->dalloc(&s->rres, (size_t)B * n));
+    const int nblk = dot_blocks(n);
+    s->partial_doubles = (long)B * (m + 1) * nblk;
+    A(s->dalloc(&s->partials, (size_t)s->partial_doubles));
+    const int64_t rw = ldc_residual_work_doubles(g);
+    A(s->dalloc(&s->res_work, (size_t)(rw > 0 ? rw : 1)));
+    A(s->dalloc(&s->ks.H, (size_t)B * (m + 1) * m));
+    A(s->dalloc(&s->ks.cs, (size_t)B * m));
+    A(s->dalloc(&s->ks.sn, (size_t)B * m));
+    A(s->dalloc(&s->ks.gv, (size_t)B * (m + 1)));
+    A(s->dalloc(&s->ks.yv, (size_t)B * m));
+    A(s->dalloc(&s->ks.hcol, (size_t)B * (m + 2)));
+    A(s->dalloc(&s->ks.hcol2, (size_t)B * (m + 2)));
+    A(s->dalloc(&s->ks.nrm2, B));
+    A(s->dalloc(&s->ks.beta, B));
+    A(s->dalloc(&s->ks.res, B));
+    A(s->dalloc(&s->ks.hnext, B));
+    A(s->dalloc(&s->run_dev, B));
+    A(s->dalloc(&s->fin_dev, B));
+    A(s->dalloc(&s->scal_dev, (size_t)3 * B));
+    A(s->halloc(&s->scal_host, (size_t)3 * B));
+    A(s->halloc(&s->res_host, B));
+    A(s->halloc(&s->du_host, B));
+    A(s->halloc(&s->mask_host, B));
+#undef A
+    if (rc != LDC_OK) {
+        ldc_solver_destroy(s);
+        return rc;
+    }
+    s->dt_host.assign(B, g->dt);
+    s->bc_host.assign(B, g->bc);
+    cudaError_t e = cudaMemcpy(s->dt_dev, s->dt_host.data(), sizeof(double) * B, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(s->bc_dev, s->bc_host.data(), sizeof(double) * B, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(s->X, 0, sizeof(double) * B * n);
+    if (e != cudaSuccess) {
+        ldc_solver_destroy(s);
+        return cuda_fail(e, "solver init", __FILE__, __LINE__);
+    }
+    s->g.dt_dev = s->dt_dev;
+    s->g.bc_dev = s->bc_dev;
+    *out = s;
+    return LDC_OK;
+}
+
+extern "C" void ldc_solver_destroy(ldc_solver *s)
+{
+    if (!s) return;
+    for (void *p : s->dev_allocs) cudaFree(p);
+    for (void *p : s->host_allocs) cudaFreeHost(p);
+    delete s;
+}
+
+extern "C" double *ldc_solver_state_dev(ldc_solver *s) { return s ? s->X : nullptr; }
+
+extern "C" int ldc_solver_num_levels(ldc_solver *s) { return s ? (int)s->levels.size() : 0; }
+
+extern "C" int ldc_solver_set_state(ldc_solver *s, const double *X_dev, void *stream)
+{
+    LDC_REQUIRE(s && X_dev, "ldc_solver_set_state: null argument");
+    LDC_CUDA(cudaMemcpyAsync(s->X, X_dev, sizeof(double) * s->batch * s->n, cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+    return LDC_OK;
+}
+
+extern "C" int ldc_solver_get_state(ldc_solver *s, double *X_dev, void *stream)
+{
+    LDC_REQUIRE(s && X_dev, "ldc_solver_get_state: null argument");
+    LDC_CUDA(cudaMemcpyAsync(X_dev, s->X, sizeof(double) * s->batch * s->n, cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+    return LDC_OK;
+}
+
+extern "C" int ldc_solver_set_dt(ldc_solver *s, const double *dt_host)
+{
+    LDC_REQUIRE(s && dt_host, "ldc_solver_set_dt: null argument");
+    for (int b = 0; b < s->batch; ++b) {
+        LDC_REQUIRE(dt_host[b] > 0.0, "dt[%d] must be positive", b);
+        s->dt_host[b] = dt_host[b];
+    }
+    LDC_CUDA(cudaMemcpy(s->dt_dev, s->dt_host.data(), sizeof(double) * s->batch, cudaMemcpyHostToDevice));
+    return LDC_OK;
+}
+
+extern "C" int ldc_solver_set_bc(ldc_solver *s, const double *bc_host)
+{
+    LDC_REQUIRE(s && bc_host, "ldc_solver_set_bc: null argument");
+    for (int b = 0; b < s->batch; ++b) s->bc_host[b] = bc_host[b];
+    LDC_CUDA(cudaMemcpy(s->bc_dev, s->bc_host.data(), sizeof(double) * s->batch, cudaMemcpyHostToDevice));
+    return LDC_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+static int upload_mask(ldc_solver *s, const std::vector<int32_t> &mask, int32_t *dst, cudaStream_t st)
+{
+    // mask_host is reused: make sure the previous upload has been consumed
+    LDC_CUDA(cudaStreamSynchronize(st));
+    for (int b = 0; b < s->batch; ++b) s->mask_host[b] = mask[b];
+    LDC_CUDA(cudaMemcpyAsync(dst, s->mask_host, sizeof(int32_t) * s->batch, cudaMemcpyHostToDevice, st));
+    return LDC_OK;
+}
+
+static bool any(const std::vector<int32_t> &m)
+{
+    for (int32_t v : m) if (v) return true;
+    return false;
+}
+
+// Jacobian at the current state on every level + diagonals
+static int build_hierarchy(ldc_solver *s, cudaStream_t st)
+{
+    for (size_t l = 0; l < s->levels.size(); ++l) {
+        MgLevel &L = s->levels[l];
+        if (l > 0) TRY(mg_restrict_state(s->levels[l - 1], L, s->batch, st));
+        ldc_grid gl = level_grid(s, L);
+        TRY(ldc_fd_jacobian(&gl, L.X, s->U_old, s->V_old, L.J, st));
+        if (s->opt.pc_type != LDC_PC_NONE) TRY(mg_extract_diag(L, s->batch, st));
+    }
+    return LDC_OK;
+}
+
+static int vcycle(ldc_solver *s, size_t l, const double *b, double *x, const int32_t *run, cudaStream_t st)
+{
+    const MgLevel &L = s->levels[l];
+    const double ou = s->opt.pc_omega_u, op = s->opt.pc_omega_p;
+    const int B = s->batch;
+    if (l + 1 == s->levels.size()) {
+        const int sweeps = (s->levels.size() == 1) ? s->opt.pc_sweeps : s->opt.mg_coarse_sweeps;
+        for (int k = 0; k < sweeps; ++k) TRY(mg_vanka_sweep(L, b, x, k == 0, ou, op, B, run, st));
+        if (s->levels.size() > 1) TRY(mg_remove_mean_pressure(L, x, B, run, nullptr, nullptr, st));
+        return LDC_OK;
+    }
+    for (int k = 0; k < s->opt.pc_sweeps; ++k) TRY(mg_vanka_sweep(L, b, x, k == 0, ou, op, B, run, st));
+    TRY(spmv_mask_launch(L.nx, L.ny, B, L.J, x, b, L.r, run, st));
+    const MgLevel &C = s->levels[l + 1];
+    TRY(mg_restrict_residual(L, L.r, C, C.b, B, run, st));
+    TRY(vcycle(s, l + 1, C.b, C.x, run, st));
+    TRY(mg_prolong_add(C, C.x, L, x, B, run, st));
+    for (int k = 0; k < s->opt.pc_sweeps; ++k) TRY(mg_vanka_sweep(L, b, x, false, ou, op, B, run, st));
+    return LDC_OK;
+}
+
+static int apply_pc(ldc_solver *s, const double *v, double *z, const int32_t *run, cudaStream_t st)
+{
+    if (s->opt.pc_type == LDC_PC_NONE) return vec_copy(v, z, s->n, s->batch, run, st);
+    TRY(vcycle(s, 0, v, z, run, st));
+    // The Jacobian is singular by the constant-pressure mode (with finite-difference
+    // noise: nearly singular).  Searching only among zero-mean pressure corrections keeps the
+    // Krylov solution out of that mode (what KSPSetNullSpace does in PETSc).
+    return mg_remove_mean_pressure(s->levels[0], z, s->batch, run, s->partials, s->ks.hcol2, st);
+}
+
+// squared norm of x per instance -> dst_dev[b]
+static int norm2_to(ldc_solver *s, const double *x, double *dst_dev, const int32_t *run, cudaStream_t st)
+{
+    const int nblk = dot_blocks(s->n);
+    TRY(vec_norm2_partials(x, s->n, s->batch, run, s->partials, st));
+    TRY(vec_reduce_partials(s->partials, 1, nblk, s->batch, dst_dev, st));
+    return LDC_OK;
+}
+
+// Solve J y = rhs for the instances flagged in `run` (host vector, modified).  bnorm = ||rhs||.
+static int fgmres(ldc_solver *s, const double *rhs, double *y, std::vector<int32_t> run,
+                  const std::vector<double> &bnorm, std::vector<int32_t> &reason,
+                  std::vector<int32_t> &its, std::vector<double> &relres, cudaStream_t st)
+{
+    const int B = s->batch, m = s->m;
+    const long n = s->n;
+    const long vs = (long)B * n;  // stride between basis vectors
+    const int nblk = dot_blocks(n);
+    const MgLevel &L0 = s->levels[0];
+    const ldc_solver_options &o = s->opt;
+    const int tb = 64, gb = (B + tb - 1) / tb;
+
+    reason.assign(B, 0);
+    its.assign(B, 0);
+    relres.assign(B, 0.0);
+    for (int b = 0; b < B; ++b)
+        if (run[b] && !(bnorm[b] > 0.0)) { run[b] = 0; reason[b] = (bnorm[b] == 0.0) ? 3 : -9; }
+    TRY(upload_mask(s, run, s->run_dev, st));
+    TRY(vec_zero(y, n, B, s->run_dev, st));
+    // r0 = rhs, beta = ||rhs||
+    TRY(vec_copy(rhs, s->rres, n, B, s->run_dev, st));
+    TRY(norm2_to(s, s->rres, s->ks.nrm2, s->run_dev, st));
+    sqrt_kernel<<<gb, tb, 0, st>>>(s->ks.nrm2, s->ks.beta, B, s->run_dev);
+    LDC_CHECK_LAUNCH();
+
+    while (any(run)) {
+        TRY(vec_scale_dev(s->rres, s->ks.beta, 1, true, s->V, n, B, s->run_dev, st));
+        krylov_begin_cycle_kernel<<<gb, tb, 0, st>>>(s->ks, m, B, s->run_dev);
+        LDC_CHECK_LAUNCH();
+        int k = 0;
+        for (; k < m && any(run); ++k) {
+            double *vk = s->V + (long)k * vs, *zk = s->Z + (long)k * vs;
+            TRY(apply_pc(s, vk, zk, s->run_dev, st));
+            TRY(spmv_mask_launch(L0.nx, L0.ny, B, L0.J, zk, nullptr, s->w, s->run_dev, st));
+            TRY(vec_multi_dot(s->V, vs, k + 1, s->w, n, B, s->run_dev, s->partials, st));
+            TRY(vec_reduce_partials(s->partials, k + 1, nblk, B, s->ks.hcol, st));
+            TRY(vec_gs_update(s->V, vs, k + 1, s->ks.hcol, k + 1, s->w, n, B, s->run_dev, s->partials, st));
+            if (o.gmres_refine) {
+                // second classical Gram-Schmidt pass (CGS2): keeps the basis orthogonal to working
+                // precision so the residual estimate stays equal to the true residual
+                TRY(vec_multi_dot(s->V, vs, k + 1, s->w, n, B, s->run_dev, s->partials, st));
+                TRY(vec_reduce_partials(s->partials, k + 1, nblk, B, s->ks.hcol2, st));
+                TRY(vec_gs_update(s->V, vs, k + 1, s->ks.hcol2, k + 1, s->w, n, B, s->run_dev, s->partials, st));
+                add_columns_kernel<<<(B * (k + 1) + 127) / 128, 128, 0, st>>>(s->ks.hcol, s->ks.hcol2, B * (k + 1));
+                LDC_CHECK_LAUNCH();
+            }
+            TRY(vec_reduce_partials(s->partials, 1, nblk, B, s->ks.nrm2, st));
+            krylov_givens_kernel<<<gb, tb, 0, st>>>(s->ks, m, k, B, s->run_dev);
+            LDC_CHECK_LAUNCH();
+            TRY(vec_scale_dev(s->w, s->ks.hnext, 1, true, s->V + (long)(k + 1) * vs, n, B, s->run_dev, st));
+            LDC_CUDA(cudaMemcpyAsync(s->res_host, s->ks.res, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+            LDC_CUDA(cudaStreamSynchronize(st));
+            std::vector<int32_t> fin(B, 0);
+            bool any_fin = false;
+            for (int b = 0; b < B; ++b) {
+                if (!run[b]) continue;
+                its[b] += 1;
+                const double r = s->res_host[b];
+                relres[b] = r / bnorm[b];
+                int rs = 0;
+                if (r != r) rs = -9;
+                else if (r <= o.ksp_atol) rs = 3;
+                else if (r <= o.ksp_rtol * bnorm[b]) rs = 2;
+                else if (r >= o.ksp_dtol * bnorm[b]) rs = -4;
+                else if (its[b] >= o.ksp_max_it) rs = -3;
+                if (rs != 0) { reason[b] = rs; fin[b] = 1; any_fin = true; }
+            }
+            if (any_fin) {
+                TRY(upload_mask(s, fin, s->fin_dev, st));
+                krylov_solve_y_kernel<<<gb, tb, 0, st>>>(s->ks, m, k + 1, B, s->fin_dev);
+                LDC_CHECK_LAUNCH();
+                TRY(vec_multi_axpy(s->Z, vs, k + 1, s->ks.yv, m, y, n, B, s->fin_dev, st));
+                for (int b = 0; b < B; ++b) if (fin[b]) run[b] = 0;
+                TRY(upload_mask(s, run, s->run_dev, st));
+            }
+        }
+        if (!any(run)) break;
+        // restart: fold the cycle into y, recompute the true residual
+        krylov_solve_y_kernel<<<gb, tb, 0, st>>>(s->ks, m, k, B, s->run_dev);
+        LDC_CHECK_LAUNCH();
+        TRY(vec_multi_axpy(s->Z, vs, k, s->ks.yv, m, y, n, B, s->run_dev, st));
+        TRY(spmv_mask_launch(L0.nx, L0.ny, B, L0.J, y, rhs, s->rres, s->run_dev, st));
+        TRY(norm2_to(s, s->rres, s->ks.nrm2, s->run_dev, st));
+        sqrt_kernel<<<gb, tb, 0, st>>>(s->ks.nrm2, s->ks.beta, B, s->run_dev);
+        LDC_CHECK_LAUNCH();
+    }
+    return LDC_OK;
+}
+
+static int residual_and_norm(ldc_solver *s, double *norm2_dst, cudaStream_t st)
+{
+    return ldc_residual(&s->g, s->X, s->U_old, s->V_old, s->F, norm2_dst, s->res_work,
+                        s->opt.residual_variant, st);
+}
+
+extern "C" int ldc_solver_linear_solve(ldc_solver *s, const double *rhs_dev, double *y_dev,
+                                       int32_t *its_host, int32_t *reason_host, double *relres_host,
+                                       void *stream)
+{
+    LDC_REQUIRE(s && rhs_dev && y_dev, "ldc_solver_linear_solve: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = s->batch;
+    std::vector<int32_t> all(B, 1);
+    TRY(upload_mask(s, all, s->run_dev, st));
+    extract_old_kernel<<<dim3((unsigned)((s->N + 255) / 256), B), 256, 0, st>>>(
+        s->g.nx, s->g.ny, s->X, s->U_old, s->V_old, s->run_dev);
+    LDC_CHECK_LAUNCH();
+    TRY(build_hierarchy(s, st));
+    TRY(norm2_to(s, rhs_dev, s->scal_dev, nullptr, st));
+    LDC_CUDA(cudaMemcpyAsync(s->scal_host, s->scal_dev, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    LDC_CUDA(cudaStreamSynchronize(st));
+    std::vector<double> bnorm(B);
+    for (int b = 0; b < B; ++b) bnorm[b] = sqrt(s->scal_host[b]);
+    std::vector<int32_t> reason, its;
+    std::vector<double> relres;
+    TRY(fgmres(s, rhs_dev, y_dev, all, bnorm, reason, its, relres, st));
+    LDC_CUDA(cudaStreamSynchronize(st));
+    for (int b = 0; b < B; ++b) {
+        if (its_host) its_host[b] = its[b];
+        if (reason_host) reason_host[b] = reason[b];
+        if (relres_host) relres_host[b] = relres[b];
+    }
+    return LDC_OK;
+}
+
+extern "C" int ldc_solver_step(ldc_solver *s, const int32_t *active_host, ldc_newton_report *rep,
+                               double *du_inf_host, void *stream)
+{
+    LDC_REQUIRE(s && rep, "ldc_solver_step: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = s->batch;
+    const long n = s->n;
+    const ldc_solver_options &o = s->opt;
+    std::vector<int32_t> act(B, 1);
+    if (active_host) for (int b = 0; b < B; ++b) act[b] = active_host[b] ? 1 : 0;
+    for (int b = 0; b < B; ++b) memset(&rep[b], 0, sizeof(ldc_newton_report));
+
+    // phi_old <- phi for the active cavities (petsc_solver_wrapper.py:53-56)
+    TRY(upload_mask(s, act, s->run_dev, st));
+    TRY(vec_copy(s->X, s->X_prev, n, B, s->run_dev, st));
+    extract_old_kernel<<<dim3((unsigned)((s->N + 255) / 256), B), 256, 0, st>>>(
+        s->g.nx, s->g.ny, s->X, s->U_old, s->V_old, s->run_dev);
+    LDC_CHECK_LAUNCH();
+
+    TRY(residual_and_norm(s, s->scal_dev, st));
+    LDC_CUDA(cudaMemcpyAsync(s->scal_host, s->scal_dev, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    LDC_CUDA(cudaStreamSynchronize(st));
+    std::vector<int32_t> run = act;
+    std::vector<double> fnorm(B, 0.0), ttol(B, 0.0);
+    for (int b = 0; b < B; ++b) {
+        if (!run[b]) continue;
+        fnorm[b] = sqrt(s->scal_host[b]);
+        rep[b].fnorm0 = rep[b].fnorm = fnorm[b];
+        rep[b].function_evaluations = 1;
+        ttol[b] = fnorm[b] * o.snes_rtol;
+        if (fnorm[b] != fnorm[b]) { rep[b].reason = -4; run[b] = 0; }
+        else if (fnorm[b] < o.snes_atol) { rep[b].reason = 2; run[b] = 0; }
+    }
+
+    for (int it = 0; it < o.snes_max_it && any(run); ++it) {
+        TRY(build_hierarchy(s, st));
+        std::vector<int32_t> kreason, kits;
+        std::vector<double> krel;
+        TRY(fgmres(s, s->F, s->Y, run, fnorm, kreason, kits, krel, st));
+        for (int b = 0; b < B; ++b) {
+            if (!run[b]) continue;
+            rep[b].function_evaluations += 21;  // what the coloured FD costs the reference
+            rep[b].linear_iterations += kits[b];
+            rep[b].ksp_reason = kreason[b];
+            s->total_linear_its += kits[b];
+            if (kreason[b] < 0) { rep[b].reason = -3; rep[b].iterations = it; run[b] = 0; }
+        }
+        if (!any(run)) break;
+        TRY(upload_mask(s, run, s->run_dev, st));
+        // full step x <- x - y (snes_linesearch_type basic)
+        TRY(vec_axpby(1.0, s->X, -1.0, s->Y, s->X, n, B, s->run_dev, st));
+        TRY(residual_and_norm(s, s->scal_dev, st));
+        TRY(norm2_to(s, s->Y, s->scal_dev + B, s->run_dev, st));
+        TRY(norm2_to(s, s->X, s->scal_dev + 2 * B, s->run_dev, st));
+        LDC_CUDA(cudaMemcpyAsync(s->scal_host, s->scal_dev, sizeof(double) * 3 * B, cudaMemcpyDeviceToHost, st));
+        LDC_CUDA(cudaStreamSynchronize(st));
+        for (int b = 0; b < B; ++b) {
+            if (!run[b]) continue;
+            fnorm[b] = sqrt(s->scal_host[b]);
+            const double ynorm = sqrt(s->scal_host[B + b]), xnorm = sqrt(s->scal_host[2 * B + b]);
+            rep[b].fnorm = fnorm[b];
+            rep[b].ynorm = ynorm;
+            rep[b].xnorm = xnorm;
+            rep[b].iterations = it + 1;
+            rep[b].function_evaluations += 1;
+            int rs = 0;
+            if (fnorm[b] != fnorm[b]) rs = -4;
+            else if (fnorm[b] < o.snes_atol) rs = 2;
+            else if (rep[b].function_evaluations >= o.snes_max_funcs) rs = -2;
+            else if (fnorm[b] <= ttol[b]) rs = 3;
+            else if (ynorm < o.snes_stol * xnorm) rs = 4;
+            else if (o.snes_divtol > 0.0 && fnorm[b] > o.snes_divtol * rep[b].fnorm0) rs = -9;
+            else if (it + 1 >= o.snes_max_it) rs = -5;
+            if (rs != 0) { rep[b].reason = rs; run[b] = 0; }
+        }
+    }
+    for (int b = 0; b < B; ++b)
+        if (act[b] && rep[b].reason == 0) rep[b].reason = -5;
+
+    // diverged cavities go back to the state they entered with (the reference raises and the
+    // time stepper retries from the old graph, time_stepper.py:23-32)
+    std::vector<int32_t> bad(B, 0);
+    for (int b = 0; b < B; ++b) bad[b] = (act[b] && rep[b].reason <= 0) ? 1 : 0;
+    if (any(bad)) {
+        TRY(upload_mask(s, bad, s->fin_dev, st));
+        TRY(vec_copy(s->X_prev, s->X, n, B, s->fin_dev, st));
+    }
+    if (du_inf_host) {
+        TRY(vec_du_inf(s->X, s->U_old, s->g.nx, s->g.ny, B, s->ks.nrm2, st));
+        LDC_CUDA(cudaMemcpyAsync(s->du_host, s->ks.nrm2, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
+    }
+    LDC_CUDA(cudaStreamSynchronize(st));
+    if (du_inf_host) for (int b = 0; b < B; ++b) du_inf_host[b] = s->du_host[b];
+    return LDC_OK;
+}

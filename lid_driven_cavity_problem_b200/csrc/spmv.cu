@@ -12,7 +12,7 @@
 //                      when that one does not fuse multiply-add).
 //   spmv_csr_kernel  : canonical CSR (indptr/indices/values) for callers that own an explicit
 //                      pattern; same flat coalesced scheme with indices read from memory.
-#include "ldc_internal.cuh"
+#include "solver_internal.cuh"
 
 namespace ldc {
 
@@ -41,8 +41,10 @@ __device__ __forceinline__ int xs_base(int k)
 
 __global__ void __launch_bounds__(kSpmvThreads)
 spmv_mask_kernel(int nx, int ny, long nnz, const double *__restrict__ values,
-                 const double *__restrict__ x, double *__restrict__ y)
+                 const double *__restrict__ x, const double *__restrict__ rhs,
+                 double *__restrict__ y, const int32_t *__restrict__ run)
 {
+    if (run && !run[blockIdx.y]) return;
     __shared__ double prod[kSpmvVals];
     __shared__ double xs[kXs];
 
@@ -51,6 +53,7 @@ spmv_mask_kernel(int nx, int ny, long nnz, const double *__restrict__ values,
     values += inst * nnz;
     x += inst * 3 * N;
     y += inst * 3 * N;
+    if (rhs) rhs += inst * 3 * N;
     const MaskGeom m{nx, N};
     const long c0 = (long)blockIdx.x * kSpmvCells;
     const long c1 = (c0 + kSpmvCells < N) ? c0 + kSpmvCells : N;
@@ -93,7 +96,7 @@ spmv_mask_kernel(int nx, int ny, long nnz, const double *__restrict__ values,
             double s = 0.0;
 #pragma unroll
             for (int k = 0; k < 21; ++k) s = __dadd_rn(s, q[k]);
-            y[3 * c0 + tid] = s;
+            y[3 * c0 + tid] = rhs ? __dsub_rn(rhs[3 * c0 + tid], s) : s;
         }
     } else {
         // boundary blocks (first/last nx cells): per-row loops over the existing offsets
@@ -110,7 +113,7 @@ spmv_mask_kernel(int nx, int ny, long nnz, const double *__restrict__ values,
                 for (int e = 0; e < 3; ++e)
                     s = __dadd_rn(s, __dmul_rn(__ldg(v + 3 * kk + e), xs[base + e]));
             }
-            y[3 * c + d] = s;
+            y[3 * c + d] = rhs ? __dsub_rn(rhs[3 * c + d], s) : s;
         }
     }
 }
@@ -153,6 +156,18 @@ spmv_csr_kernel(long n_rows, const int32_t *__restrict__ indptr, const int32_t *
 
 }  // namespace ldc
 
+namespace ldc {
+int spmv_mask_launch(int nx, int ny, int batch, const double *values, const double *x,
+                     const double *b, double *y, const int32_t *run, cudaStream_t s)
+{
+    const long N = (long)nx * ny;
+    dim3 grid((unsigned)((N + kSpmvCells - 1) / kSpmvCells), batch);
+    spmv_mask_kernel<<<grid, kSpmvThreads, 0, s>>>(nx, ny, ldc_mask_nnz(nx, ny, 3), values, x, b, y, run);
+    LDC_CHECK_LAUNCH();
+    return LDC_OK;
+}
+}  // namespace ldc
+
 using namespace ldc;
 
 extern "C" int ldc_spmv_mask(const ldc_grid *g, const double *values_dev, const double *x_dev,
@@ -160,12 +175,8 @@ extern "C" int ldc_spmv_mask(const ldc_grid *g, const double *values_dev, const 
 {
     if (int rc = validate_grid(g, true)) return rc;
     LDC_REQUIRE(values_dev && x_dev && y_dev && x_dev != y_dev, "ldc_spmv_mask: bad device pointers");
-    const long N = (long)g->nx * g->ny;
-    dim3 grid((unsigned)((N + kSpmvCells - 1) / kSpmvCells), g->batch);
-    spmv_mask_kernel<<<grid, kSpmvThreads, 0, (cudaStream_t)stream>>>(
-        g->nx, g->ny, ldc_mask_nnz(g->nx, g->ny, 3), values_dev, x_dev, y_dev);
-    LDC_CHECK_LAUNCH();
-    return LDC_OK;
+    return spmv_mask_launch(g->nx, g->ny, g->batch, values_dev, x_dev, nullptr, y_dev, nullptr,
+                            (cudaStream_t)stream);
 }
 
 extern "C" int ldc_spmv_csr(int64_t n_rows, const int32_t *indptr_dev, const int32_t *indices_dev,
