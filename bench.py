@@ -1,0 +1,416 @@
+"""Benchmark of the lid-driven-cavity hot path on B200 (contract: see the round prompt).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-solve]
+
+Metric (BASELINE.json): residual Mcells/s in fp64 and its fraction of the HBM roofline, plus the
+time-to-converge of the 1024x1024 Re=1000 steady solve (extra key ``time_to_converge``).
+
+One *step* = one residual evaluation F(X) of a 1024x1024 cavity per GPU on the synthetic inputs of
+SURVEY 8(d), inputs resident in HBM, L2-cold by rotating through buffer sets whose total size is
+several times the 126 MB L2.  With N > 1 GPUs the global grid is 1024 x (1024*N), decomposed into
+row strips (one per rank) with a one-row halo exchange per evaluation (weak scaling).
+``e2e`` is the same evaluation through the reference-facing plug-in
+``cuda_residual_function.residual_function(X_numpy, graph)``: host buffers in, host buffer out,
+host<->device copies inside the timed region.
+``--impl reference`` times the reference's own C++-OpenMP residual (oracle/_ref, compiled
+unchanged from c++/residual_function_omp.cpp) on the box's host cores for the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+NX = NY = 1024
+RE = 1000.0
+
+
+def synthetic_case(nx, ny, bc=RE, dt=1e-2, seed=None):
+    """SURVEY 8(d) synthetic throughput inputs (mixed signs exercise all upwind branches)."""
+    from lid_driven_cavity_problem_b200.staggered_grid import Graph
+    rng = np.random.default_rng(1000 + nx if seed is None else seed)
+    g = Graph(1.0, 1.0, nx, ny, dt, 1.0, 1.0, bc)
+    U = bc * rng.uniform(-1, 1, (nx - 1) * ny)
+    V = bc * rng.uniform(-1, 1, nx * (ny - 1))
+    P = bc * bc * rng.uniform(-1, 1, nx * ny)
+    g.ns_x_mesh.phi, g.ns_y_mesh.phi, g.pressure_mesh.phi = U, V, P
+    g.ns_x_mesh.phi_old = 0.9 * U
+    g.ns_y_mesh.phi_old = 0.9 * V
+    X = np.zeros(3 * nx * ny)
+    X[0::3] = P
+    Xu = np.zeros((ny, nx))
+    Xu[:, :nx - 1] = U.reshape(ny, nx - 1)
+    X[1::3] = Xu.ravel()
+    X[2:3 * nx * (ny - 1):3] = V
+    return g, X
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json')))['hbm_gbs']), 'measured'
+    except Exception:
+        return 6650.0, 'fallback'
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = float(r[1])
+                for k, nme in enumerate(names):
+                    if r[3 + k].lower().startswith('active'):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_residual(seconds_budget=12.0, nx=NX, ny=NY):
+    """reference C++-OpenMP residual through its pybind11 entry (the reference path, Python
+    overhead included), all host threads; returns (Mcells/s best-of-N, cores, kind, sample)."""
+    from oracle import ldc_oracle as orc
+    cores = os.cpu_count() or 1
+    os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+    g, X = synthetic_case(nx, ny)
+    try:
+        ref = orc.ref_module()
+        fn, kind = (lambda: ref.residual_function_omp(X, g)), 'reference'
+    except Exception:
+        fn, kind = (lambda: orc.residual_function(X, g, nthreads=0)), 'port'
+    fn()
+    times, t_start = [], time.time()
+    while time.time() - t_start < seconds_budget and len(times) < 200:
+        t0 = time.perf_counter()
+        fn()
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    sample = '%d calls of residual_function%s on %dx%d synthetic inputs, best wall time' % (
+        len(times), '_omp (c++/residual_function_omp.cpp, g++ -O2 -fopenmp)' if kind == 'reference' else ' (oracle port)', nx, ny)
+    return nx * ny / best / 1e6, cores, kind, sample, best
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    warm, steps = max(args.warmup, 1), max(args.steps, 1)
+    from oracle import ldc_oracle as orc
+    cores = os.cpu_count() or 1
+    os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+    g, X = synthetic_case(NX, NY)
+    try:
+        ref = orc.ref_module()
+        fn, kind = (lambda: ref.residual_function_omp(X, g)), 'reference'
+    except Exception:
+        fn, kind = (lambda: orc.residual_function(X, g, nthreads=0)), 'port'
+    for _ in range(warm):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt = (time.perf_counter() - t0) / steps
+    # the reference is one process: with N "GPUs" it still evaluates one 1024x1024 cavity per step
+    val = NX * NY / dt / 1e6
+    line = {
+        "impl": "reference", "metric": "residual_mcells_per_s", "value": val, "unit": "Mcells/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "residual F(X) of one 1024x1024 Re=1000 cavity (SURVEY 8d inputs), "
+                               "reference C++-OpenMP residual on host cores", "grid": [NX, NY]},
+        "cpu_baseline": {"value": val, "unit": "Mcells/s", "cores": cores, "kind": kind,
+                         "sample": "%d calls of %s through its Python entry" % (
+                             steps, 'c++/residual_function_omp.cpp (g++ -O2 -fopenmp)' if kind == 'reference'
+                             else 'the oracle port')},
+        "e2e": {"value": val, "unit": "Mcells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def time_to_converge(max_seconds=120.0):
+    """reference demo recipe at 1024^2 Re=1000 (run_solver.py:42-67): Graph(1,1,n,n,dt=1e-2,rho=1,
+    mi=1,bc=Re), P=U=V=1 start, run_simulation(final_time=None), wall clock around it incl. setup."""
+    import torch
+    from lid_driven_cavity_problem_b200.nonlinear_solver import cuda_solver_wrapper
+    from lid_driven_cavity_problem_b200.staggered_grid import Graph
+    from lid_driven_cavity_problem_b200.time_stepper import run_simulation
+    wrapper = cuda_solver_wrapper.CudaSolverWrapper(None)
+    graph = Graph(1.0, 1.0, NX, NY, 1e-2, 1.0, 1.0, RE)
+    steps = []
+    torch.cuda.synchronize()
+    t0 = time.time()
+
+    def on_step(g, t):
+        steps.append(t)
+        if time.time() - t0 > max_seconds:
+            raise TimeoutError()
+    status = 'converged (reference steady test: max|U-U_old|/bc < 1e-6)'
+    try:
+        run_simulation(graph, None, wrapper.solve, on_step=on_step)
+    except TimeoutError:
+        status = 'stopped after %.0f s' % max_seconds
+    torch.cuda.synchronize()
+    sec = time.time() - t0
+    wrapper.close()
+    return {"grid": "%dx%d" % (NX, NY), "Re": RE, "seconds": round(sec, 3), "status": status,
+            "time_steps": len(steps), "newton_iterations": wrapper.total_newton_iterations,
+            "krylov_iterations": wrapper.total_linear_iterations,
+            "residual_evaluations_equivalent": wrapper.total_function_evaluations,
+            "pseudo_time": steps[-1] if steps else 0.0}
+
+
+def cpu_solve_sample(budget=25.0):
+    """Bounded sample of the reference path for the solve (PETSc-equivalent restatement, PETSc is
+    not installable): one FD Jacobian + ILU(0) + a few GMRES(30) iterations of the FIRST Newton
+    iteration at 1024^2 Re=1000.  Returns per-unit costs; the full run would need
+    ~(krylov its) x (s per Krylov it), hours."""
+    from oracle import ldc_oracle as orc
+    from lid_driven_cavity_problem_b200.staggered_grid import Graph
+    g = Graph(1.0, 1.0, NX, NY, 1e-2, 1.0, 1.0, RE)
+    X = orc.create_X(g.ns_x_mesh.phi, g.ns_y_mesh.phi, g.pressure_mesh.phi, g)
+    t0 = time.time()
+    mask = orc.jacobian_mask_arrays(NX, NY, 3)
+    t_mask = time.time() - t0
+    t0 = time.time()
+    F = orc.residual_function(X, g, nthreads=0)
+    J = orc.fd_jacobian(X, g, F0=F, mask=mask, nthreads=0)
+    t_jac = time.time() - t0
+    t0 = time.time()
+    lu, diag, _, _ = orc.ilu0(mask, J)
+    t_ilu = time.time() - t0
+    its = 8
+    t0 = time.time()
+    _, reason, kits, rn = orc.gmres_ilu0(mask, J, lu, diag, F, max_it=its, nthreads=0)
+    t_gm = (time.time() - t0) / max(kits, 1)
+    return {"kind": "port (PETSc-equivalent restatement; PETSc/petsc4py not installable)",
+            "cores": os.cpu_count(), "mask_s": round(t_mask, 3), "fd_jacobian_s": round(t_jac, 3),
+            "ilu0_factor_s": round(t_ilu, 3), "s_per_gmres_iteration": round(t_gm, 4),
+            "sample": "1024x1024 Re=1000, first Newton iteration: mask + 21-colour FD Jacobian + ILU(0) "
+                      "+ %d GMRES(30) iterations" % kits}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='cuda')
+    ap.add_argument('--no-solve', action='store_true', help='skip the time-to-converge run')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline legs')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from lid_driven_cavity_problem_b200 import _native
+    from lid_driven_cavity_problem_b200.residual_function import cuda_residual_function as crf
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    lib = _native.lib()
+    warm, steps = max(args.warmup, 3), max(args.steps, 1)
+
+    # ---- workload: strip `rank` of a 1024 x (1024*world) cavity
+    nx, ny_local = NX, NY
+    ny_global = NY * world
+    g, X = synthetic_case(nx, ny_local, seed=1000 + nx + rank)
+    g_strip = g  # scalars only
+    N = nx * ny_local
+    res_bytes = 8 * (8 * N - nx - ny_local)
+    n_sets = 9  # 9 x 67 MB = 604 MB of inputs+outputs in rotation >> 126 MB L2
+    row = 3 * nx
+    # each set: [ghost row below | owned rows | ghost row above]
+    Xbuf = [torch.zeros(row * (ny_local + 2), dtype=torch.float64, device='cuda') for _ in range(n_sets)]
+    for k in range(n_sets):
+        Xbuf[k][row:row * (ny_local + 1)] = torch.from_numpy(X).cuda() + float(k)
+    Fs = [torch.empty(3 * N, dtype=torch.float64, device='cuda') for _ in range(n_sets)]
+    Ud = [torch.from_numpy(g.ns_x_mesh.phi_old).cuda().clone() for _ in range(n_sets)]
+    Vfull = np.concatenate([g.ns_y_mesh.phi_old, 0.9 * RE * np.ones(nx)])  # strip-local V_old has ny_local rows unless top strip
+    Vd = [torch.from_numpy(Vfull).cuda().clone() for _ in range(n_sets)]
+    grid = _native.LdcGrid()
+    grid.nx, grid.ny = nx, ny_global
+    grid.row_begin, grid.row_count = rank * ny_local, ny_local
+    grid.batch, grid.use_cds = 1, 0
+    grid.dt, grid.dx, grid.dy = 1e-2, 1.0 / nx, 1.0 / ny_global
+    grid.rho, grid.mi, grid.bc = 1.0, 1.0, RE
+    stream = _native.current_stream()
+
+    def halo_exchange(k):
+        if world == 1:
+            return
+        buf = Xbuf[k]
+        ops = []
+        if rank > 0:
+            ops.append(dist.P2POp(dist.isend, buf[row:2 * row], rank - 1))
+            ops.append(dist.P2POp(dist.irecv, buf[0:row], rank - 1))
+        if rank < world - 1:
+            ops.append(dist.P2POp(dist.isend, buf[row * ny_local:row * (ny_local + 1)], rank + 1))
+            ops.append(dist.P2POp(dist.irecv, buf[row * (ny_local + 1):], rank + 1))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    def step(k):
+        halo_exchange(k)
+        rc = lib.ldc_residual(grid, Xbuf[k].data_ptr() + 8 * row, _native.ptr(Ud[k]), _native.ptr(Vd[k]),
+                              _native.ptr(Fs[k]), None, None, 0, stream)
+        if rc != 0:
+            _native.check(rc, 'ldc_residual')
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(warm):
+        step(k % n_sets)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for k in range(steps):
+        step(k % n_sets)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    # keep the GPU busy long enough for the clock sampler to see it under load
+    if rank == 0:
+        t_end = time.time() + 0.6
+        k = 0
+        while time.time() < t_end:
+            step(k % n_sets)
+            k += 1
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / steps
+    value = N * world / (ms_step * 1e-3) / 1e6
+
+    # ---- kernel-only roofline (single launch stream, CUDA events, no halo exchange)
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev2.record()
+    for k in range(steps):
+        lib.ldc_residual(grid, Xbuf[k % n_sets].data_ptr() + 8 * row, _native.ptr(Ud[k % n_sets]),
+                         _native.ptr(Vd[k % n_sets]), _native.ptr(Fs[k % n_sets]), None, None, 0, stream)
+    ev3.record()
+    torch.cuda.synchronize()
+    kern_ms = ev2.elapsed_time(ev3) / steps
+    peak, peak_kind = hbm_peak()
+    achieved = res_bytes / (kern_ms * 1e-3) / 1e9
+
+    # ---- e2e through the plug-in (host numpy in, host numpy out)
+    g_e2e, X_e2e = synthetic_case(NX, NY)
+    e2e_steps = max(5, min(steps, 30))
+    for _ in range(3):
+        crf.residual_function(X_e2e, g_e2e)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        F_host = crf.residual_function(X_e2e, g_e2e)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    n_unknowns = 3 * NX * NY
+    h2d = 8 * (n_unknowns + (NX - 1) * NY + NX * (NY - 1))
+    d2h = 8 * n_unknowns
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": "residual_mcells_per_s", "value": value, "unit": "Mcells/s", "n_gpus": world,
+        "steps": steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "residual F(X) of a 1024x1024 Re=1000 cavity per GPU (SURVEY 8d synthetic "
+                               "inputs); N>1: row strips of a 1024x(1024*N) grid with a one-row NCCL halo "
+                               "exchange per evaluation",
+                   "grid_per_gpu": [NX, NY], "l2": "L2-cold: rotating %d buffer sets (%.0f MB) > 126 MB L2" % (
+                       n_sets, n_sets * res_bytes / 1e6),
+                   "kernel": "residual_march_kernel (flux form, bit-exact arithmetic)"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                     "algorithmic_bytes_per_launch": res_bytes, "kernel_ms": kern_ms},
+        "e2e": {"value": NX * NY * world / e2e_s / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_call": e2e_s * 1e3,
+                "api": "cuda_residual_function.residual_function(X_numpy, graph) -> numpy"},
+        "gpu_launches": steps,
+        "clocks": clocks,
+    }
+    if not args.no_cpu:
+        v, cores, kind, sample, best = cpu_reference_residual()
+        line["cpu_baseline"] = {"value": v, "unit": "Mcells/s", "cores": cores, "kind": kind, "sample": sample}
+    if world == 1 and not args.no_solve:
+        try:
+            line["time_to_converge"] = time_to_converge()
+            if not args.no_cpu:
+                line["time_to_converge"]["cpu_reference_sample"] = cpu_solve_sample()
+        except Exception as e:  # the solve is an extra; never lose the headline line
+            line["time_to_converge"] = {"error": repr(e)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
