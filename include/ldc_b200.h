@@ -61,7 +61,8 @@ LDC_API int ldc_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_mi
  * the five sibling backends.  F_dev is fully overwritten (dummy rows F=X).  When
  * norm2_dev != NULL, *norm2_dev receives sum(F^2) per instance ([batch] doubles), computed by a
  * deterministic two-stage reduction (work_dev must then hold ldc_residual_work_doubles()).
- * variant: 0 = auto, 1 = cell-per-thread reference kernel, 2 = flux-form column-marching kernel.
+ * variant: 0 = auto, 1 = cell-per-thread reference kernel, 2 = flux-form column-marching kernel,
+ *          3 = flux form with TMA-staged rows (needs even nx and 16-byte aligned X, else falls back to 2).
  */
 LDC_API int64_t ldc_residual_work_doubles(const ldc_grid *g);
 LDC_API int ldc_residual(const ldc_grid *g, const double *X_dev, const double *U_old_dev,

@@ -5,10 +5,12 @@
 // pure-Python siblings.  Arithmetic is evaluated in the reference's order with exactly-rounded
 // fp64 operations (no FMA contraction), so results are bit-identical to the x86-64 -O2 build.
 //
-// Two kernels:
-//   residual_cell_kernel  : one thread per cell, direct transcription of the three row formulas
+// Three kernels (ldc_residual `variant`):
+//   1 residual_cell_kernel  : one thread per cell, direct transcription of the three row formulas
 //                           (shares them with the FD-Jacobian kernel).
-//   residual_march_kernel : flux form.  The scheme is conservative: the advective and diffusive
+//   3 residual_tma_kernel   : variant 2's arithmetic with the rows streamed through a shared-memory
+//                           ring by TMA bulk copies (producer warp + mbarriers).
+//   2 residual_march_kernel : flux form (default).  The scheme is conservative: the advective and diffusive
 //                           flux through a face is the SAME expression for the two cells that
 //                           share it (the reference evaluates it twice).  Each lane owns one
 //                           grid column and marches up a tile of rows; it evaluates only the
@@ -21,6 +23,9 @@
 
 namespace ldc {
 
+#ifndef LDC_MARCH_MIN_BLOCKS
+#define LDC_MARCH_MIN_BLOCKS 4
+#endif
 static constexpr int kMarchWarps = 4;                 // warps per block
 static constexpr int kMarchCols = 30;                 // output columns per warp (lanes 1..30)
 
@@ -128,68 +133,137 @@ __device__ __forceinline__ CellVals load_cell(const double *__restrict__ X, int 
 __device__ __forceinline__ double shfl_down1(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 __device__ __forceinline__ double shfl_up1(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 
-template <bool POW2>
-__global__ void __launch_bounds__(kMarchWarps * 32)
-residual_march_kernel(const ldc_grid g, const double *__restrict__ X,
-                      const double *__restrict__ U_old, const double *__restrict__ V_old,
-                      double *__restrict__ F, double *__restrict__ partials, int rows_per_tile)
+// Face fluxes.  FAST = (dx, dy powers of two) && (rho == mi == 1): multiplying by 1.0 is the
+// identity and power-of-two scalings commute with rounding (normal range), so
+//   mi*((a-b)/dx)*dy == (a-b)*(dy/dx)   and   rho*((va+vb)/2)*phi*len == ((va+vb)*(len/2))*phi
+// bit for bit, at a third of the fp64 instructions.  The generic branch keeps the literal order.
+// Upwinding: (.5-beta)*a + (.5+beta)*b with beta=+-.5 is 0*a + 1*b or 1*a + 0*b, i.e. a select
+// (identical up to the sign of a zero result).
+template <bool POW2, bool FAST, bool CDS>
+struct FluxOps {
+    const Phys &p;
+    double kx, ky, hx, hy;   // dy/dx, dx/dy, dx/2, dy/2 (FAST only)
+    __device__ __forceinline__ explicit FluxOps(const Phys &ph) : p(ph)
+    {
+        kx = dmul(ph.inv_dx, ph.dy);
+        ky = dmul(ph.inv_dy, ph.dx);
+        hx = dmul(0.5, ph.dx);
+        hy = dmul(0.5, ph.dy);
+    }
+    __device__ __forceinline__ double interp(double vel, double phi_a, double phi_b) const
+    {
+        if (CDS) return dadd(dmul(0.5, phi_a), dmul(0.5, phi_b));
+        return vel > 0.0 ? phi_b : phi_a;
+    }
+    // diffusive flux through an x-normal face (length dy) / a y-normal face (length dx)
+    __device__ __forceinline__ double dif_x(double a, double b) const
+    {
+        if (FAST) return dmul(dsub(a, b), kx);
+        return dmul(dmul(p.mi, over_dx<POW2>(dsub(a, b), p)), p.dy);
+    }
+    __device__ __forceinline__ double dif_y(double a, double b) const
+    {
+        if (FAST) return dmul(dsub(a, b), ky);
+        return dmul(dmul(p.mi, over_dy<POW2>(dsub(a, b), p)), p.dx);
+    }
+    // advective flux of phi through an x-normal face: rho*((va+vb)/2)*interp*dy
+    __device__ __forceinline__ double adv_x(double va, double vb, double phi_a, double phi_b) const
+    {
+        if (FAST) {
+            const double vl = dmul(dadd(va, vb), hy);
+            return dmul(vl, interp(vl, phi_a, phi_b));
+        }
+        const double vel = dmul(dadd(va, vb), 0.5);
+        return dmul(dmul(dmul(p.rho, vel), interp(vel, phi_a, phi_b)), p.dy);
+    }
+    __device__ __forceinline__ double adv_y(double va, double vb, double phi_a, double phi_b) const
+    {
+        if (FAST) {
+            const double vl = dmul(dadd(va, vb), hx);
+            return dmul(vl, interp(vl, phi_a, phi_b));
+        }
+        const double vel = dmul(dadd(va, vb), 0.5);
+        return dmul(dmul(dmul(p.rho, vel), interp(vel, phi_a, phi_b)), p.dx);
+    }
+    __device__ __forceinline__ double transient(double phi, double phi_old) const
+    {
+        if (FAST) return dmul(dsub(phi, phi_old), p.vol_dt);
+        return dmul(dsub(dmul(p.rho, phi), dmul(p.rho, phi_old)), p.vol_dt);
+    }
+};
+
+// One tile of rows for one block.  INTERIOR: no lane of the block touches a wall, the lid, a
+// dummy slot or a missing ghost row, so every mask below folds away at compile time.
+template <bool POW2, bool FAST, bool CDS, bool INTERIOR>
+__device__ __forceinline__ double march_tile(const ldc_grid &g, const Phys &p,
+                                             const double *__restrict__ X,
+                                             const double *__restrict__ U_old,
+                                             const double *__restrict__ V_old,
+                                             double *__restrict__ F, int i, int lane, int jl0, int jl1)
 {
-    const int inst = blockIdx.z;
-    const Strides st = instance_strides(g);
-    X += inst * st.x;
-    F += inst * st.x;
-    U_old += inst * st.u;
-    V_old += inst * st.v;
-    const Phys p = make_phys(g, inst);
-
+    const FluxOps<POW2, FAST, CDS> fx(p);
     const int nx = g.nx, ny = g.ny;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = (blockIdx.x * kMarchWarps + warp) * kMarchCols - 1 + lane;  // grid column
-    const int jl0 = blockIdx.y * rows_per_tile;
-    const int jl1 = min(jl0 + rows_per_tile, g.row_count);
-    const bool writer = lane >= 1 && lane <= kMarchCols && i < nx;  // i >= 0 for lane >= 1
-    const bool u_col = i >= 0 && i < nx - 1;   // column holds a real U
-    const bool side_wall = i < 0 || i >= nx - 1;  // U_NE of the V rows is forced to 0 here
+    const bool writer = lane >= 1 && lane <= kMarchCols && (INTERIOR || i < nx);
+    const bool in_grid = INTERIOR || (i >= 0 && i < nx);
+    const bool u_col = INTERIOR || (i >= 0 && i < nx - 1);
+    const bool side_wall = !INTERIOR && (i < 0 || i >= nx - 1);
 
-    // a local row jl is readable if it is an owned row or an existing ghost row
     auto row_ok = [&](int jl) {
+        if (INTERIOR) return true;
         const int jg = g.row_begin + jl;
         return jg >= 0 && jg < ny && jl >= -1 && jl <= g.row_count;
     };
-    // masked (wall-aware) views of a raw cell at grid row jg
+    const long row_stride = 3L * nx;
+    const double *xcol = X + 3L * i;   // column i of local row 0 (may point before X for i = -1)
+    auto load = [&](int jl, bool ok) {
+        CellVals c;
+        if (INTERIOR || (ok && in_grid)) {
+            const double *q = xcol + row_stride * jl;
+            c.P = __ldg(q);
+            c.U = __ldg(q + 1);
+            c.V = __ldg(q + 2);
+        } else {
+            c.P = 0.0; c.U = 0.0; c.V = 0.0;
+        }
+        return c;
+    };
     auto Um = [&](const CellVals &c) { return u_col ? c.U : 0.0; };
-    auto Vm = [&](const CellVals &c, int jg) { return (jg < ny - 1) ? c.V : 0.0; };
+    auto Vm = [&](const CellVals &c, int jg) { return (INTERIOR || (jg >= 0 && jg < ny - 1)) ? c.V : 0.0; };
 
     // ---- prologue: south faces of the first row = north faces of row jl0-1
-    CellVals S = load_cell(X, i, jl0 - 1, nx, row_ok(jl0 - 1));
-    CellVals C = load_cell(X, i, jl0, nx, row_ok(jl0));
-    CellVals N = load_cell(X, i, jl0 + 1, nx, row_ok(jl0 + 1));
+    CellVals S = load(jl0 - 1, row_ok(jl0 - 1));
+    CellVals C = load(jl0, row_ok(jl0));
+    CellVals N = load(jl0 + 1, row_ok(jl0 + 1));
+    CellVals N2 = load(jl0 + 2, (jl0 + 2 <= jl1) && row_ok(jl0 + 2));
     double AU_s, DU_s, AV_s, DV_s, CV_s;
     {
-        const int jg = g.row_begin + jl0 - 1;  // may be -1: everything below the floor is 0
-        const double Sm_U = Um(S), Sm_V = (jg >= 0) ? Vm(S, jg) : 0.0;
+        const int jg = g.row_begin + jl0 - 1;
+        const double Sm_U = Um(S), Sm_V = Vm(S, jg);
         const double Cm_U = Um(C), Cm_V = Vm(C, jg + 1);
         const double Sm_Ve = shfl_down1(Sm_V);
-        // U rows: north face of (i, jg)   [U_N is never the lid here: jg < ny-1]
-        const double dU_n = over_dy<POW2>(dsub(Cm_U, Sm_U), p);
-        const double vn = dmul(dadd(Sm_Ve, Sm_V), 0.5);
-        AU_s = adv_flux(vn, Cm_U, Sm_U, p.dx, p);
-        DU_s = dmul(dmul(p.mi, dU_n), p.dx);
-        // V rows
-        const double dV_n = over_dy<POW2>(dsub(Cm_V, Sm_V), p);
-        const double vvn = dmul(dadd(Sm_V, Cm_V), 0.5);
-        AV_s = adv_flux(vvn, Cm_V, Sm_V, p.dx, p);
-        DV_s = dmul(dmul(p.mi, dV_n), p.dx);
+        AU_s = fx.adv_y(Sm_Ve, Sm_V, Cm_U, Sm_U);   // V_s=(V_SE+V_SW)/2 carries U
+        DU_s = fx.dif_y(Cm_U, Sm_U);
+        AV_s = fx.adv_y(Sm_V, Cm_V, Cm_V, Sm_V);    // V_s=(V_S+V_P)/2 carries V
+        DV_s = fx.dif_y(Cm_V, Sm_V);
         CV_s = dmul(Sm_V, p.dx);
     }
 
+    const double *uo = U_old + i + (long)(nx - 1) * jl0;
+    const double *vo = V_old + i + (long)nx * jl0;
+    double *out = F + 3L * i + row_stride * jl0;
     double sq = 0.0;
-    for (int jl = jl0; jl < jl1; ++jl) {
+    // old values are prefetched one row ahead, X rows three rows ahead: ~13 doubles per lane in
+    // flight, which is what it takes to cover HBM latency at ~16 warps per SM
+    double Uold_n = u_col ? __ldg(uo) : 0.0;
+    double Vold_n = (INTERIOR || (in_grid && g.row_begin + jl0 < ny - 1)) ? __ldg(vo) : 0.0;
+    for (int jl = jl0; jl < jl1; ++jl, uo += nx - 1, vo += nx, out += row_stride) {
         const int jg = g.row_begin + jl;
-        // prefetch row jl+2 and this row's old values before the arithmetic
-        const CellVals NN = load_cell(X, i, jl + 2, nx, (jl + 2 <= jl1) && row_ok(jl + 2));
-        const double Uold = (u_col) ? __ldg(U_old + i + (long)(nx - 1) * jl) : 0.0;
-        const double Vold = (i >= 0 && i < nx && jg < ny - 1) ? __ldg(V_old + i + (long)nx * jl) : 0.0;
+        const CellVals N3 = load(jl + 3, (jl + 3 <= jl1) && row_ok(jl + 3));
+        const double Uold = Uold_n, Vold = Vold_n;
+        if (jl + 1 < jl1) {
+            Uold_n = u_col ? __ldg(uo + (nx - 1)) : 0.0;
+            Vold_n = (INTERIOR || (in_grid && jg + 1 < ny - 1)) ? __ldg(vo + nx) : 0.0;
+        }
 
         const double Cm_U = Um(C), Cm_V = Vm(C, jg);
         const double Nm_U = Um(N), Nm_V = Vm(N, jg + 1);
@@ -198,27 +272,19 @@ residual_march_kernel(const ldc_grid g, const double *__restrict__ X,
         const double C_Pe = shfl_down1(C.P);
 
         // ---- north face of (i, jg)
-        const double U_N = (jg == ny - 1) ? p.bc : Nm_U;
-        const double dU_n = over_dy<POW2>(dsub(U_N, Cm_U), p);
-        const double vn = dmul(dadd(Cm_Ve, Cm_V), 0.5);
-        const double AU_n = adv_flux(vn, U_N, Cm_U, p.dx, p);
-        const double DU_n = dmul(dmul(p.mi, dU_n), p.dx);
-        const double dV_n = over_dy<POW2>(dsub(Nm_V, Cm_V), p);
-        const double vvn = dmul(dadd(Cm_V, Nm_V), 0.5);
-        const double AV_n = adv_flux(vvn, Nm_V, Cm_V, p.dx, p);
-        const double DV_n = dmul(dmul(p.mi, dV_n), p.dx);
+        const double U_N = (!INTERIOR && jg == ny - 1) ? p.bc : Nm_U;
+        const double AU_n = fx.adv_y(Cm_Ve, Cm_V, U_N, Cm_U);
+        const double DU_n = fx.dif_y(U_N, Cm_U);
+        const double AV_n = fx.adv_y(Cm_V, Nm_V, Nm_V, Cm_V);
+        const double DV_n = fx.dif_y(Nm_V, Cm_V);
         const double CV_n = dmul(Cm_V, p.dx);
 
         // ---- east face of (i, jg)
-        const double dU_e = over_dx<POW2>(dsub(Cm_Ue, Cm_U), p);
-        const double ue = dmul(dadd(Cm_Ue, Cm_U), 0.5);
-        const double AU_e = adv_flux(ue, Cm_Ue, Cm_U, p.dy, p);
-        const double DU_e = dmul(dmul(p.mi, dU_e), p.dy);
-        const double U_NE = side_wall ? 0.0 : ((jg == ny - 2) ? p.bc : Nm_U);
-        const double uue = dmul(dadd(U_NE, Cm_U), 0.5);
-        const double dV_e = over_dx<POW2>(dsub(Cm_Ve, Cm_V), p);
-        const double AV_e = adv_flux(uue, Cm_Ve, Cm_V, p.dy, p);
-        const double DV_e = dmul(dmul(p.mi, dV_e), p.dy);
+        const double AU_e = fx.adv_x(Cm_Ue, Cm_U, Cm_Ue, Cm_U);
+        const double DU_e = fx.dif_x(Cm_Ue, Cm_U);
+        const double U_NE = side_wall ? 0.0 : ((!INTERIOR && jg == ny - 2) ? p.bc : Nm_U);
+        const double AV_e = fx.adv_x(U_NE, Cm_U, Cm_Ve, Cm_V);
+        const double DV_e = fx.dif_x(Cm_Ve, Cm_V);
         const double CU_e = dmul(Cm_U, p.dy);
 
         // ---- west face = east face of the lane to the left
@@ -232,7 +298,7 @@ residual_march_kernel(const ldc_grid g, const double *__restrict__ X,
             const double f0 = dadd(dsub(CU_e, CU_w), dsub(CV_n, CV_s));
             double f1, f2;
             if (u_col) {
-                const double tr = dmul(dsub(dmul(p.rho, Cm_U), dmul(p.rho, Uold)), p.vol_dt);
+                const double tr = fx.transient(Cm_U, Uold);
                 const double adv = dsub(dadd(dsub(AU_e, AU_w), AU_n), AU_s);
                 const double dif = dsub(dadd(dsub(DU_e, DU_w), DU_n), DU_s);
                 const double src = dmul(-dsub(C_Pe, C.P), p.dy);
@@ -240,8 +306,8 @@ residual_march_kernel(const ldc_grid g, const double *__restrict__ X,
             } else {
                 f1 = C.U;  // dummy row: F = X
             }
-            if (jg < ny - 1) {
-                const double tr = dmul(dsub(dmul(p.rho, Cm_V), dmul(p.rho, Vold)), p.vol_dt);
+            if (INTERIOR || jg < ny - 1) {
+                const double tr = fx.transient(Cm_V, Vold);
                 const double adv = dsub(dadd(dsub(AV_e, AV_w), AV_n), AV_s);
                 const double dif = dsub(dadd(dsub(DV_e, DV_w), DV_n), DV_s);
                 const double src = dmul(-dsub(N.P, C.P), p.dx);
@@ -249,7 +315,6 @@ residual_march_kernel(const ldc_grid g, const double *__restrict__ X,
             } else {
                 f2 = C.V;
             }
-            double *out = F + 3L * ((long)i + (long)nx * jl);
             out[0] = f0;
             out[1] = f1;
             out[2] = f2;
@@ -257,8 +322,40 @@ residual_march_kernel(const ldc_grid g, const double *__restrict__ X,
         }
         AU_s = AU_n; DU_s = DU_n; AV_s = AV_n; DV_s = DV_n; CV_s = CV_n;
         C = N;
-        N = NN;
+        N = N2;
+        N2 = N3;
     }
+    return sq;
+}
+
+template <bool POW2, bool FAST, bool CDS>
+__global__ void __launch_bounds__(kMarchWarps * 32, LDC_MARCH_MIN_BLOCKS)
+residual_march_kernel(const ldc_grid g, const double *__restrict__ X,
+                      const double *__restrict__ U_old, const double *__restrict__ V_old,
+                      double *__restrict__ F, double *__restrict__ partials, int rows_per_tile)
+{
+    const int inst = blockIdx.z;
+    const Strides st = instance_strides(g);
+    X += inst * st.x;
+    F += inst * st.x;
+    U_old += inst * st.u;
+    V_old += inst * st.v;
+    const Phys p = make_phys(g, inst);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i_first = blockIdx.x * kMarchWarps * kMarchCols - 1;   // column of lane 0, warp 0
+    const int i = i_first + warp * kMarchCols + lane;
+    const int jl0 = blockIdx.y * rows_per_tile;
+    const int jl1 = min(jl0 + rows_per_tile, g.row_count);
+    // block-uniform: columns [i_first, i_first + 4*30 + 1] within [0, nx-3], rows jg-1..jg+1 of the
+    // tile strictly inside (no wall, no lid, no dummy V row)
+    const int i_last = i_first + (kMarchWarps - 1) * kMarchCols + 31;
+    const int jg0 = g.row_begin + jl0, jg1 = g.row_begin + jl1;
+    const bool interior = i_first >= 0 && i_last <= g.nx - 3 && jg0 >= 1 && jg1 <= g.ny - 2;
+
+    double sq;
+    if (interior) sq = march_tile<POW2, FAST, CDS, true>(g, p, X, U_old, V_old, F, i, lane, jl0, jl1);
+    else sq = march_tile<POW2, FAST, CDS, false>(g, p, X, U_old, V_old, F, i, lane, jl0, jl1);
 
     if (partials) {
 #pragma unroll
@@ -269,6 +366,298 @@ residual_march_kernel(const ldc_grid g, const double *__restrict__ X,
         if (threadIdx.x == 0) {
             double t = 0.0;
             for (int w = 0; w < kMarchWarps; ++w) t += warp_sums[w];
+            const long nblk = (long)gridDim.x * gridDim.y;
+            partials[(long)inst * nblk + (long)blockIdx.y * gridDim.x + blockIdx.x] = t;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// variant 3: flux form, rows streamed through a shared-memory ring by TMA bulk copies.
+// Same arithmetic as variant 2; the data movement is decoupled from the compute warps:
+//   * a producer warp (one elected lane) issues one cp.async.bulk per grid row of the block's
+//     column strip into a ring of kTmaRing row slabs, each completing on its own mbarrier
+//     ("full"); compute warps release a slab through an "empty" mbarrier when the row is done;
+//   * ~20 KB per block are in flight regardless of occupancy and registers (variant 2 has to
+//     hold its prefetched rows in registers), DRAM/L2 see only whole aligned lines instead of
+//     stride-3 sector fragments, lanes read the interleaved cells from shared memory (stride of
+//     3 doubles is bank-conflict free) and stage F per warp so global stores are contiguous.
+// Needs nx even and a 16-byte aligned X (row starts are then 16-byte aligned); otherwise the
+// launcher falls back to variant 2.
+// ---------------------------------------------------------------------------------------------
+static constexpr int kTmaWarps = 4;                               // compute warps (+1 producer warp)
+static constexpr int kTmaColsPerWarp = 31;                        // lane 0 only provides the west face
+static constexpr int kTmaCols = kTmaWarps * kTmaColsPerWarp;      // 124 output columns per block
+static constexpr int kTmaSlab = 384;                              // doubles per staged row (126 cells + pad)
+static constexpr int kTmaRing = 8;                                // row slabs in the ring
+static constexpr int kTmaStage = 96;                              // doubles of F staging per warp and buffer
+static constexpr int kTmaThreads = (kTmaWarps + 1) * 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+
+template <bool POW2, bool FAST, bool CDS>
+__global__ void __launch_bounds__(kTmaThreads)
+residual_tma_kernel(const ldc_grid g, const double *__restrict__ X,
+                    const double *__restrict__ U_old, const double *__restrict__ V_old,
+                    double *__restrict__ F, double *__restrict__ partials, int rows_per_tile)
+{
+    __shared__ __align__(128) double slabs[kTmaRing * kTmaSlab];
+    __shared__ __align__(16) double stage[2 * kTmaWarps * kTmaStage];
+    __shared__ uint64_t full_bar[kTmaRing], empty_bar[kTmaRing];
+    __shared__ double warp_sums[kTmaWarps];
+
+    const int inst = blockIdx.z;
+    const Strides st = instance_strides(g);
+    X += inst * st.x;
+    F += inst * st.x;
+    U_old += inst * st.u;
+    V_old += inst * st.v;
+    const Phys p = make_phys(g, inst);
+    const FluxOps<POW2, FAST, CDS> fx(p);
+
+    const int nx = g.nx, ny = g.ny;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c0 = blockIdx.x * kTmaCols;
+    const int jl0 = blockIdx.y * rows_per_tile;
+    const int jl1 = min(jl0 + rows_per_tile, g.row_count);
+    const int nslab = jl1 - jl0 + 2;                          // local rows jl0-1 .. jl1
+
+    // accessible local rows: owned rows plus the ghost rows that exist in the grid
+    const int row_lo = (g.row_begin > 0) ? -1 : 0;
+    const int row_hi = g.row_count + ((g.row_begin + g.row_count < ny) ? 1 : 0);  // exclusive
+    // first staged double of local row jl (even -> 16-byte aligned because nx is even)
+    auto slab_d0 = [&](int jl) {
+        long s0 = (long)(c0 - 1) + (long)nx * jl;
+        const long lo_cell = (long)nx * row_lo;
+        if (s0 < lo_cell) s0 = lo_cell;
+        return (3 * s0) & ~1L;
+    };
+
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < kTmaRing; ++r) {
+            mbar_init(full_bar + r, 1);
+            mbar_init(empty_bar + r, kTmaWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    double sq = 0.0;
+    if (warp == kTmaWarps) {
+        // ===== producer: one lane streams the rows of this column strip through the ring
+        if (lane == 0) {
+            const long hi_cell = (long)nx * row_hi;
+            for (int k = 0; k < nslab; ++k) {
+                const int slot = k % kTmaRing;
+                if (k >= kTmaRing) mbar_wait(empty_bar + slot, ((k / kTmaRing) - 1) & 1);
+                const int jl = jl0 - 1 + k;
+                if (jl < row_lo || jl >= row_hi) {       // row outside the grid: nothing to load
+                    mbar_expect_tx(full_bar + slot, 0);
+                    continue;
+                }
+                const long d0 = slab_d0(jl);
+                long b = (long)(c0 - 1) + (long)nx * jl + kTmaCols + 2;
+                if (b > hi_cell) b = hi_cell;
+                const long d1 = (3 * b + 1) & ~1L;
+                const uint32_t bytes = (uint32_t)((d1 - d0) * 8);
+                mbar_expect_tx(full_bar + slot, bytes);
+                bulk_g2s(slabs + (size_t)slot * kTmaSlab, X + d0, bytes, full_bar + slot);
+            }
+        }
+    } else {
+        // ===== compute warps
+        const int i = c0 - 1 + warp * kTmaColsPerWarp + lane;   // grid column of this lane
+        const bool writer = lane >= 1 && i < nx;
+        const bool in_grid = i >= 0 && i < nx;
+        const bool e_grid = i + 1 >= 0 && i + 1 < nx;
+        const bool u_col = i >= 0 && i < nx - 1;
+        const bool side_wall = i < 0 || i >= nx - 1;
+        auto wait_row = [&](int jl) {
+            const int k = jl - (jl0 - 1);
+            mbar_wait(full_bar + (k % kTmaRing), (k / kTmaRing) & 1);
+        };
+        auto release_row = [&](int jl) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_bar + ((jl - (jl0 - 1)) % kTmaRing));
+        };
+        // this lane's cell inside the slab of local row jl; every dereference is guarded by the
+        // column predicates (q[0..2] need in_grid, q[3..5] need e_grid) and the row predicates
+        auto cell_ptr = [&](int jl) -> const double * {
+            const long off = 3 * ((long)i + (long)nx * jl) - slab_d0(jl);
+            return slabs + (long)((jl - (jl0 - 1)) % kTmaRing) * kTmaSlab + off;
+        };
+        auto row_ok = [&](int jl) { return jl >= row_lo && jl < row_hi; };
+
+        // ---- prologue: south faces of the first row = north faces of row jl0-1
+        double C_P = 0.0, C_U = 0.0, C_V = 0.0;      // raw own cell of the current row
+        double AU_s, DU_s, AV_s, DV_s, CV_s;
+        {
+            const int jg = g.row_begin + jl0 - 1;
+            double S_U = 0.0, S_V = 0.0, S_Ve = 0.0;
+            wait_row(jl0 - 1);
+            if (row_ok(jl0 - 1)) {
+                const double *q = cell_ptr(jl0 - 1);
+                if (u_col) S_U = q[1];
+                if (in_grid && jg < ny - 1) S_V = q[2];
+                if (e_grid && jg < ny - 1) S_Ve = q[5];
+            }
+            release_row(jl0 - 1);
+            wait_row(jl0);   // row jl0 is always an owned row
+            {
+                const double *q = cell_ptr(jl0);
+                if (in_grid) { C_P = q[0]; C_U = q[1]; C_V = q[2]; }
+            }
+            const double Cm_U = u_col ? C_U : 0.0;
+            const double Cm_V = (jg + 1 < ny - 1) ? C_V : 0.0;
+            AU_s = fx.adv_y(S_Ve, S_V, Cm_U, S_U);
+            DU_s = fx.dif_y(Cm_U, S_U);
+            AV_s = fx.adv_y(S_V, Cm_V, Cm_V, S_V);
+            DV_s = fx.dif_y(Cm_V, S_V);
+            CV_s = dmul(S_V, p.dx);
+        }
+
+        const double *uo = U_old + i + (long)(nx - 1) * jl0;
+        const double *vo = V_old + i + (long)nx * jl0;
+        double Uold_n = u_col ? __ldg(uo) : 0.0;
+        double Vold_n = (in_grid && g.row_begin + jl0 < ny - 1) ? __ldg(vo) : 0.0;
+        double *my_stage = stage + (size_t)warp * kTmaStage;
+        const int first_col = c0 + warp * kTmaColsPerWarp;   // first output column of this warp
+        int out_doubles = 3 * (nx - first_col);
+        if (out_doubles > 3 * kTmaColsPerWarp) out_doubles = 3 * kTmaColsPerWarp;
+
+        for (int jl = jl0; jl < jl1; ++jl, uo += nx - 1, vo += nx) {
+            const int jg = g.row_begin + jl;
+            const double Uold = Uold_n, Vold = Vold_n;
+            if (jl + 1 < jl1) {   // prefetch next row's old values
+                Uold_n = u_col ? __ldg(uo + (nx - 1)) : 0.0;
+                Vold_n = (in_grid && jg + 1 < ny - 1) ? __ldg(vo + nx) : 0.0;
+            }
+            // east neighbour of the current row (its slab is complete since the previous iteration)
+            double Ce_P = 0.0, Ce_U = 0.0, Ce_V = 0.0;
+            {
+                const double *q = cell_ptr(jl);
+                if (e_grid) { Ce_P = q[3]; Ce_U = q[4]; Ce_V = q[5]; }
+            }
+            // own cell of the row above
+            double N_P = 0.0, N_U = 0.0, N_V = 0.0;
+            wait_row(jl + 1);
+            if (row_ok(jl + 1)) {
+                const double *q = cell_ptr(jl + 1);
+                if (in_grid) { N_P = q[0]; N_U = q[1]; N_V = q[2]; }
+            }
+            release_row(jl);   // all reads of slab jl are done (values are in registers)
+
+            const double Cm_U = u_col ? C_U : 0.0;
+            const double Cm_V = (jg < ny - 1) ? C_V : 0.0;
+            const double Nm_U = u_col ? N_U : 0.0;
+            const double Nm_V = (jg + 1 < ny - 1) ? N_V : 0.0;
+            const double Cm_Ue = (i + 1 < nx - 1) ? Ce_U : 0.0;
+            const double Cm_Ve = (jg < ny - 1) ? Ce_V : 0.0;
+
+            // ---- north face
+            const double U_N = (jg == ny - 1) ? p.bc : Nm_U;
+            const double AU_n = fx.adv_y(Cm_Ve, Cm_V, U_N, Cm_U);
+            const double DU_n = fx.dif_y(U_N, Cm_U);
+            const double AV_n = fx.adv_y(Cm_V, Nm_V, Nm_V, Cm_V);
+            const double DV_n = fx.dif_y(Nm_V, Cm_V);
+            const double CV_n = dmul(Cm_V, p.dx);
+            // ---- east face
+            const double AU_e = fx.adv_x(Cm_Ue, Cm_U, Cm_Ue, Cm_U);
+            const double DU_e = fx.dif_x(Cm_Ue, Cm_U);
+            const double U_NE = side_wall ? 0.0 : ((jg == ny - 2) ? p.bc : Nm_U);
+            const double AV_e = fx.adv_x(U_NE, Cm_U, Cm_Ve, Cm_V);
+            const double DV_e = fx.dif_x(Cm_Ve, Cm_V);
+            const double CU_e = dmul(Cm_U, p.dy);
+            // ---- west face = east face of the lane to the left
+            const double AU_w = shfl_up1(AU_e);
+            const double DU_w = shfl_up1(DU_e);
+            const double AV_w = shfl_up1(AV_e);
+            const double DV_w = shfl_up1(DV_e);
+            const double CU_w = shfl_up1(CU_e);
+
+            double *sbuf = my_stage + (size_t)((jl - jl0) & 1) * kTmaWarps * kTmaStage;
+            if (writer) {
+                const double f0 = dadd(dsub(CU_e, CU_w), dsub(CV_n, CV_s));
+                double f1, f2;
+                if (u_col) {
+                    const double tr = fx.transient(Cm_U, Uold);
+                    const double adv = dsub(dadd(dsub(AU_e, AU_w), AU_n), AU_s);
+                    const double dif = dsub(dadd(dsub(DU_e, DU_w), DU_n), DU_s);
+                    const double src = dmul(-dsub(Ce_P, C_P), p.dy);
+                    f1 = dsub(dsub(dadd(tr, adv), dif), src);
+                } else {
+                    f1 = C_U;
+                }
+                if (jg < ny - 1) {
+                    const double tr = fx.transient(Cm_V, Vold);
+                    const double adv = dsub(dadd(dsub(AV_e, AV_w), AV_n), AV_s);
+                    const double dif = dsub(dadd(dsub(DV_e, DV_w), DV_n), DV_s);
+                    const double src = dmul(-dsub(N_P, C_P), p.dx);
+                    f2 = dsub(dsub(dadd(tr, adv), dif), src);
+                } else {
+                    f2 = C_V;
+                }
+                sbuf[3 * (lane - 1)] = f0;
+                sbuf[3 * (lane - 1) + 1] = f1;
+                sbuf[3 * (lane - 1) + 2] = f2;
+                sq += f0 * f0 + f1 * f1 + f2 * f2;
+            }
+            __syncwarp();
+            if (out_doubles > 0) {   // contiguous store of the warp's 93 doubles of this row
+                double *out = F + 3L * ((long)first_col + (long)nx * jl);
+#pragma unroll
+                for (int t = lane; t < 3 * kTmaColsPerWarp; t += 32)
+                    if (t < out_doubles) out[t] = sbuf[t];
+            }
+            AU_s = AU_n; DU_s = DU_n; AV_s = AV_n; DV_s = DV_n; CV_s = CV_n;
+            C_P = N_P; C_U = N_U; C_V = N_V;
+        }
+        // the last slab (row jl1) was only read: nothing waits for it
+    }
+
+    if (partials) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0 && warp < kTmaWarps) warp_sums[warp] = sq;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < kTmaWarps; ++w) t += warp_sums[w];
             const long nblk = (long)gridDim.x * gridDim.y;
             partials[(long)inst * nblk + (long)blockIdx.y * gridDim.x + blockIdx.x] = t;
         }
@@ -316,6 +705,28 @@ static MarchPlan plan_march(const ldc_grid &g)
     return pl;
 }
 
+// rows per tile for the ring kernel: tall tiles amortise the pipeline fill (2 rows) and the halo
+// row; the candidate with the best balance of blocks over resident slots wins.
+static MarchPlan plan_tma(const ldc_grid &g)
+{
+    const int col_blocks = (g.nx + kTmaCols - 1) / kTmaCols;
+    const long slots = (long)sm_count() * 3;   // ~3 blocks of 160 threads per SM (registers)
+    int best_rows = g.row_count < 8 ? g.row_count : 8;
+    double best_score = -1.0;
+    for (int rows = 8; rows <= 128 && rows <= g.row_count; ++rows) {
+        const long blocks = (long)col_blocks * ((g.row_count + rows - 1) / rows) * g.batch;
+        const long waves = (blocks + slots - 1) / slots;
+        const double balance = (double)blocks / (double)(waves * slots);
+        const double fill = (double)rows / (double)(rows + 3.0);
+        const double score = balance * fill;
+        if (score > best_score) { best_score = score; best_rows = rows; }
+    }
+    MarchPlan pl;
+    pl.rows_per_tile = best_rows;
+    pl.grid = dim3(col_blocks, (g.row_count + best_rows - 1) / best_rows, g.batch);
+    return pl;
+}
+
 static long cell_blocks(const ldc_grid &g) { return ((long)g.nx * g.row_count + 255) / 256; }
 
 }  // namespace ldc
@@ -326,9 +737,13 @@ extern "C" int64_t ldc_residual_work_doubles(const ldc_grid *g)
 {
     if (!g || validate_grid(g, false) != 0) return -1;
     const MarchPlan pl = plan_march(*g);
-    const long a = (long)pl.grid.x * pl.grid.y;
+    const MarchPlan pt = plan_tma(*g);
+    long a = (long)pl.grid.x * pl.grid.y;
     const long b = cell_blocks(*g);
-    return (a > b ? a : b) * g->batch;
+    const long c = (long)pt.grid.x * pt.grid.y;
+    if (b > a) a = b;
+    if (c > a) a = c;
+    return a * g->batch;
 }
 
 extern "C" int ldc_residual(const ldc_grid *g, const double *X_dev, const double *U_old_dev,
@@ -339,13 +754,32 @@ extern "C" int ldc_residual(const ldc_grid *g, const double *X_dev, const double
     LDC_REQUIRE(X_dev && U_old_dev && V_old_dev && F_dev, "ldc_residual: null device pointer");
     LDC_REQUIRE(X_dev != F_dev, "ldc_residual: F must not alias X");
     LDC_REQUIRE(!norm2_dev || work_dev, "ldc_residual: norm2 requested without work buffer");
-    LDC_REQUIRE(variant >= 0 && variant <= 2, "ldc_residual: unknown variant %d", variant);
+    LDC_REQUIRE(variant >= 0 && variant <= 3, "ldc_residual: unknown variant %d", variant);
     cudaStream_t s = (cudaStream_t)stream;
     const bool pow2 = is_pow2_double(g->dx) && is_pow2_double(g->dy);
     double *partials = norm2_dev ? work_dev : nullptr;
     long per_instance;
-    if (variant == 0) variant = 2;
-    if (variant == 1) {
+    const bool tma_ok = (g->nx % 2 == 0) && (((uintptr_t)X_dev & 15) == 0) && g->row_count >= 2;
+    if (variant == 0) variant = 2;   // measured on B200: 2 beats 3 at every size (profiles/r1_sweep_c*)
+    if (variant == 3 && !tma_ok) variant = 2;
+    if (variant == 3) {
+        const MarchPlan pl = plan_tma(*g);
+        per_instance = (long)pl.grid.x * pl.grid.y;
+        const bool fast = pow2 && g->rho == 1.0 && g->mi == 1.0;
+#define LDC_LAUNCH_TMA(P2, FA, CD)                                                          \
+    residual_tma_kernel<P2, FA, CD><<<pl.grid, kTmaThreads, 0, s>>>(*g, X_dev, U_old_dev, V_old_dev, \
+                                                                 F_dev, partials, pl.rows_per_tile)
+        if (g->use_cds) {
+            if (fast) LDC_LAUNCH_TMA(true, true, true);
+            else if (pow2) LDC_LAUNCH_TMA(true, false, true);
+            else LDC_LAUNCH_TMA(false, false, true);
+        } else {
+            if (fast) LDC_LAUNCH_TMA(true, true, false);
+            else if (pow2) LDC_LAUNCH_TMA(true, false, false);
+            else LDC_LAUNCH_TMA(false, false, false);
+        }
+#undef LDC_LAUNCH_TMA
+    } else if (variant == 1) {
         dim3 grid((unsigned)cell_blocks(*g), 1, g->batch);
         per_instance = grid.x;
         if (pow2)
@@ -355,12 +789,22 @@ extern "C" int ldc_residual(const ldc_grid *g, const double *X_dev, const double
     } else {
         const MarchPlan pl = plan_march(*g);
         per_instance = (long)pl.grid.x * pl.grid.y;
-        if (pow2)
-            residual_march_kernel<true><<<pl.grid, kMarchWarps * 32, 0, s>>>(
-                *g, X_dev, U_old_dev, V_old_dev, F_dev, partials, pl.rows_per_tile);
-        else
-            residual_march_kernel<false><<<pl.grid, kMarchWarps * 32, 0, s>>>(
-                *g, X_dev, U_old_dev, V_old_dev, F_dev, partials, pl.rows_per_tile);
+        // FAST needs exact unit density/viscosity; per-instance dt/bc do not matter
+        const bool fast = pow2 && g->rho == 1.0 && g->mi == 1.0;
+        const dim3 blk(kMarchWarps * 32);
+#define LDC_LAUNCH_MARCH(P2, FA, CD)                                                     \
+    residual_march_kernel<P2, FA, CD><<<pl.grid, blk, 0, s>>>(*g, X_dev, U_old_dev, V_old_dev, \
+                                                             F_dev, partials, pl.rows_per_tile)
+        if (g->use_cds) {
+            if (fast) LDC_LAUNCH_MARCH(true, true, true);
+            else if (pow2) LDC_LAUNCH_MARCH(true, false, true);
+            else LDC_LAUNCH_MARCH(false, false, true);
+        } else {
+            if (fast) LDC_LAUNCH_MARCH(true, true, false);
+            else if (pow2) LDC_LAUNCH_MARCH(true, false, false);
+            else LDC_LAUNCH_MARCH(false, false, false);
+        }
+#undef LDC_LAUNCH_MARCH
     }
     LDC_CHECK_LAUNCH();
     if (norm2_dev) {

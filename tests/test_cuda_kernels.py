@@ -20,7 +20,7 @@ def cuda():
 def _residual_variants(cuda, X, g):
     torch, crf = cuda['torch'], cuda['crf']
     Xd = torch.from_numpy(X).cuda()
-    return [crf.residual_function_device(Xd, g, variant=v).cpu().numpy() for v in (1, 2)]
+    return [crf.residual_function_device(Xd, g, variant=v).cpu().numpy() for v in (1, 2, 3)]
 
 
 def test_reference_3x3_known_answer(cuda, golden):
@@ -41,7 +41,7 @@ def test_golden_random_cases_bit_exact(cuda, golden):
         g = make_graph(d['params_%d' % k], 0.9, d['U_%d' % k], d['V_%d' % k], d['P_%d' % k])
         for tag in ('', '_dummy'):
             X, F = d['X%s_%d' % (tag, k)], d['F%s_%d' % (tag, k)]
-            for v, Fv in zip((1, 2), _residual_variants(cuda, X, g)):
+            for v, Fv in zip((1, 2, 3), _residual_variants(cuda, X, g)):
                 assert np.array_equal(Fv, F), (k, tag, v)
         # packing
         common = cuda['common']
@@ -51,12 +51,13 @@ def test_golden_random_cases_bit_exact(cuda, golden):
         assert np.array_equal(P, d['P_%d' % k])
 
 
-@pytest.mark.parametrize("nx,ny", [(100, 100), (256, 256), (257, 131), (1024, 1024), (61, 1030)])
+@pytest.mark.parametrize("nx,ny", [(100, 100), (256, 256), (257, 131), (1024, 1024), (61, 1030), (124, 9),
+                                   (126, 40), (250, 33), (4, 3), (2048, 64)])
 def test_residual_vs_oracle(cuda, nx, ny):
     from oracle import ldc_oracle as orc
     g, X = synthetic_case(nx, ny)
     F_ref = orc.residual_function(X, g, nthreads=0)
-    for v, Fv in zip((1, 2), _residual_variants(cuda, X, g)):
+    for v, Fv in zip((1, 2, 3), _residual_variants(cuda, X, g)):
         # north_star: 1e-12 relative (normwise); the kernels are in fact bit-exact
         assert np.abs(Fv - F_ref).max() <= 1e-12 * np.abs(F_ref).max(), (nx, ny, v)
         assert np.array_equal(Fv, F_ref), (nx, ny, v)
@@ -71,7 +72,7 @@ def test_residual_fused_norm(cuda):
     for nx, ny in [(100, 100), (513, 300)]:
         g, X = synthetic_case(nx, ny)
         Xd = torch.from_numpy(X).cuda()
-        for v in (1, 2):
+        for v in (1, 2, 3):
             n2 = torch.zeros(1, dtype=torch.float64, device='cuda')
             F = crf.residual_function_device(Xd, g, variant=v, norm2_out=n2)
             ref = float(np.dot(F.cpu().numpy(), F.cpu().numpy()))
@@ -97,7 +98,7 @@ def test_residual_batch_ensemble(cuda):
     Xd = torch.from_numpy(np.concatenate(Xs)).cuda()
     Ud = torch.from_numpy(np.concatenate(Us)).cuda()
     Vd = torch.from_numpy(np.concatenate(Vs)).cuda()
-    for v in (1, 2):
+    for v in (1, 2, 3):
         F = torch.empty_like(Xd)
         native.check(native.lib().ldc_residual(grid, native.ptr(Xd), native.ptr(Ud), native.ptr(Vd),
                                                native.ptr(F), None, None, v, native.current_stream()))
@@ -114,7 +115,7 @@ def test_residual_row_strips(cuda):
     U_old = g.ns_x_mesh.phi_old.reshape(ny, nx - 1)
     V_old = g.ns_y_mesh.phi_old.reshape(ny - 1, nx)
     bounds = [0, 17, 18, 40, 70]
-    for v in (1, 2):
+    for v in (1, 2, 3):
         out = np.empty_like(F_ref)
         for j0, j1 in zip(bounds[:-1], bounds[1:]):
             lo, hi = max(j0 - 1, 0), min(j1 + 1, ny)
