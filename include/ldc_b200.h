@@ -88,6 +88,14 @@ LDC_API int ldc_mask_csr(int32_t nx, int32_t ny, int32_t dof, int32_t *indptr_de
 LDC_API int ldc_fd_jacobian(const ldc_grid *g, const double *X_dev, const double *U_old_dev,
                     const double *V_old_dev, double *values_dev, void *stream);
 
+/* Same Jacobian in the solver's compact layout: the 26 entries per cell a row can really depend
+ * on (4 continuity + 11 + 11 momentum; the other 37 mask entries are exact zeros), stored
+ * compact_dev[k*N + c], k order documented in csrc/jacobian.cu.  26*N*batch doubles. */
+LDC_API int ldc_fd_jacobian_compact(const ldc_grid *g, const double *X_dev, const double *U_old_dev,
+                                    const double *V_old_dev, double *compact_dev, void *stream);
+LDC_API int ldc_spmv_compact(const ldc_grid *g, const double *compact_dev, const double *x_dev,
+                             double *y_dev, void *stream);
+
 /* ---- SpMV y = J x on the mask pattern: replaces MatMult_SeqAIJ.
  * ldc_spmv_mask uses the closed-form structure (no index arrays are read);
  * ldc_spmv_csr is the canonical CSR product (reads indptr/indices). */

@@ -63,6 +63,8 @@ SYMBOLS = {
     'ldc_mask_nnz': (_i64, [_i32, _i32, _i32]),
     'ldc_mask_csr': (ctypes.c_int, [_i32, _i32, _i32, _vp, _vp, _vp]),
     'ldc_fd_jacobian': (ctypes.c_int, [_grid_p, _vp, _vp, _vp, _vp, _vp]),
+    'ldc_fd_jacobian_compact': (ctypes.c_int, [_grid_p, _vp, _vp, _vp, _vp, _vp]),
+    'ldc_spmv_compact': (ctypes.c_int, [_grid_p, _vp, _vp, _vp, _vp]),
     'ldc_spmv_mask': (ctypes.c_int, [_grid_p, _vp, _vp, _vp, _vp]),
     'ldc_spmv_csr': (ctypes.c_int, [_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     'ldc_solver_default_options': (None, [ctypes.POINTER(LdcSolverOptions)]),

@@ -40,17 +40,19 @@ restrict_state_kernel(int nxf, int nyf, const double *__restrict__ Xf, double *_
     Xc[3 * c + 2] = (J < nyc - 1) ? 0.5 * (f(i0, j0 + 1, 2) + f(i0 + 1, j0 + 1, 2)) : 0.0;
 }
 
+// diagonal of J from the compact layout: U rows -> k=9 (U_P), V rows -> k=20 (V_P); continuity
+// rows have no diagonal (0)
 __global__ void __launch_bounds__(256)
-extract_diag_kernel(int nx, int ny, long nnz, const double *__restrict__ J, double *__restrict__ diag)
+extract_diag_kernel(long N, const double *__restrict__ Jc, double *__restrict__ diag)
 {
-    const long N = (long)nx * ny;
-    const long r = (long)blockIdx.x * 256 + threadIdx.x;
-    if (r >= 3 * N) return;
+    const long c = (long)blockIdx.x * 256 + threadIdx.x;
+    if (c >= N) return;
     const int b = blockIdx.y;
-    const MaskGeom m{nx, N};
-    const long c = r / 3;
-    const int d = (int)(r - 3 * c);
-    diag[(long)b * 3 * N + r] = J[(long)b * nnz + m.row_start(c, d) + 3 * (3 - m.lo_missing(c)) + d];
+    Jc += (long)b * 26 * N;
+    double *d = diag + (long)b * 3 * N + 3 * c;
+    d[0] = 0.0;
+    d[1] = Jc[9 * N + c];
+    d[2] = Jc[20 * N + c];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -294,7 +296,7 @@ int mg_restrict_state(const MgLevel &f, const MgLevel &c, int batch, cudaStream_
 
 int mg_extract_diag(const MgLevel &l, int batch, cudaStream_t s)
 {
-    extract_diag_kernel<<<cell_grid(l.n, batch), 256, 0, s>>>(l.nx, l.ny, l.nnz, l.J, l.diag);
+    extract_diag_kernel<<<cell_grid(l.N, batch), 256, 0, s>>>(l.N, l.J, l.diag);
     LDC_CHECK_LAUNCH();
     return LDC_OK;
 }
@@ -304,7 +306,7 @@ int mg_vanka_sweep(const MgLevel &l, const double *b, double *x, bool zero_guess
 {
     const double *r = b;
     if (!zero_guess) {
-        if (int rc = spmv_mask_launch(l.nx, l.ny, batch, l.J, x, b, l.r, run, s)) return rc;
+        if (int rc = spmv_compact_launch(l.nx, l.ny, batch, l.J, x, b, l.r, run, s)) return rc;
         r = l.r;
     }
     vanka_dp_kernel<<<cell_grid(l.N, batch), 256, 0, s>>>(l.nx, l.ny, l.dx, l.dy, r, l.diag, l.dp, run);

@@ -287,7 +287,7 @@ extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *op
             A(s->dalloc(&L.x, (size_t)B * L.n));
             A(s->dalloc(&L.b, (size_t)B * L.n));
         }
-        A(s->dalloc(&L.J, (size_t)B * L.nnz));
+        A(s->dalloc(&L.J, (size_t)B * 26 * L.N));
         A(s->dalloc(&L.diag, (size_t)B * L.n));
         A(s->dalloc(&L.r, (size_t)B * L.n));
         A(s->dalloc(&L.dp, (size_t)B * L.N));
@@ -410,7 +410,7 @@ static int build_hierarchy(ldc_solver *s, cudaStream_t st)
         MgLevel &L = s->levels[l];
         if (l > 0) TRY(mg_restrict_state(s->levels[l - 1], L, s->batch, st));
         ldc_grid gl = level_grid(s, L);
-        TRY(ldc_fd_jacobian(&gl, L.X, s->U_old, s->V_old, L.J, st));
+        TRY(fd_jacobian_launch(&gl, L.X, s->U_old, s->V_old, nullptr, L.J, st));
         if (s->opt.pc_type != LDC_PC_NONE) TRY(mg_extract_diag(L, s->batch, st));
     }
     return LDC_OK;
@@ -428,7 +428,7 @@ static int vcycle(ldc_solver *s, size_t l, const double *b, double *x, const int
         return LDC_OK;
     }
     for (int k = 0; k < s->opt.pc_sweeps; ++k) TRY(mg_vanka_sweep(L, b, x, k == 0, ou, op, B, run, st));
-    TRY(spmv_mask_launch(L.nx, L.ny, B, L.J, x, b, L.r, run, st));
+    TRY(spmv_compact_launch(L.nx, L.ny, B, L.J, x, b, L.r, run, st));
     const MgLevel &C = s->levels[l + 1];
     TRY(mg_restrict_residual(L, L.r, C, C.b, B, run, st));
     TRY(vcycle(s, l + 1, C.b, C.x, run, st));
@@ -490,7 +490,7 @@ static int fgmres(ldc_solver *s, const double *rhs, double *y, std::vector<int32
         for (; k < m && any(run); ++k) {
             double *vk = s->V + (long)k * vs, *zk = s->Z + (long)k * vs;
             TRY(apply_pc(s, vk, zk, s->run_dev, st));
-            TRY(spmv_mask_launch(L0.nx, L0.ny, B, L0.J, zk, nullptr, s->w, s->run_dev, st));
+            TRY(spmv_compact_launch(L0.nx, L0.ny, B, L0.J, zk, nullptr, s->w, s->run_dev, st));
             TRY(vec_multi_dot(s->V, vs, k + 1, s->w, n, B, s->run_dev, s->partials, st));
             TRY(vec_reduce_partials(s->partials, k + 1, nblk, B, s->ks.hcol, st));
             TRY(vec_gs_update(s->V, vs, k + 1, s->ks.hcol, k + 1, s->w, n, B, s->run_dev, s->partials, st));
@@ -538,7 +538,7 @@ static int fgmres(ldc_solver *s, const double *rhs, double *y, std::vector<int32
         krylov_solve_y_kernel<<<gb, tb, 0, st>>>(s->ks, m, k, B, s->run_dev);
         LDC_CHECK_LAUNCH();
         TRY(vec_multi_axpy(s->Z, vs, k, s->ks.yv, m, y, n, B, s->run_dev, st));
-        TRY(spmv_mask_launch(L0.nx, L0.ny, B, L0.J, y, rhs, s->rres, s->run_dev, st));
+        TRY(spmv_compact_launch(L0.nx, L0.ny, B, L0.J, y, rhs, s->rres, s->run_dev, st));
         TRY(norm2_to(s, s->rres, s->ks.nrm2, s->run_dev, st));
         sqrt_kernel<<<gb, tb, 0, st>>>(s->ks.nrm2, s->ks.beta, B, s->run_dev);
         LDC_CHECK_LAUNCH();

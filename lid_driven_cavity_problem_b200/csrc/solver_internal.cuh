@@ -44,11 +44,19 @@ int vec_norm2_partials(const double *x, long n, int batch, const int32_t *run, d
 int vec_du_inf(const double *x, const double *U_old, int nx, int ny, int batch, double *out,
                cudaStream_t s);
 
+// ---- jacobian.cu ---------------------------------------------------------------------------
+// coloured-FD Jacobian into the CSR(mask) value array and/or the compact 26-entry SoA layout
+int fd_jacobian_launch(const ldc_grid *g, const double *X, const double *U_old, const double *V_old,
+                       double *csr_values, double *compact, cudaStream_t st);
+
 // ---- spmv.cu (internal entry with residual form) -------------------------------------------
 // y = J x            (b == nullptr)
 // y = b - J x        (b != nullptr)
 int spmv_mask_launch(int nx, int ny, int batch, const double *values, const double *x,
                      const double *b, double *y, const int32_t *run, cudaStream_t s);
+// same on the compact layout Jc[26][N] (see jacobian.cu)
+int spmv_compact_launch(int nx, int ny, int batch, const double *Jc, const double *x,
+                        const double *b, double *y, const int32_t *run, cudaStream_t s);
 
 // ---- precond.cu ----------------------------------------------------------------------------
 struct MgLevel {
@@ -56,7 +64,7 @@ struct MgLevel {
     double dx, dy;
     long N, n, nnz;
     double *X;       // state the level's Jacobian is linearised about   [batch*n]
-    double *J;       // CSR(mask) values                                  [batch*nnz]
+    double *J;       // compact Jacobian Jc[26][N] (jacobian.cu)            [batch*26*N]
     double *diag;    // diagonal of J                                     [batch*n]
     double *x, *b, *r;  // correction, right-hand side, residual          [batch*n]
     double *dp;      // cell pressure corrections of the relaxation       [batch*N]

@@ -206,3 +206,50 @@ def test_inputs_are_validated(cuda):
     X0 = X.copy()
     crf.residual_function(X, g)
     assert np.array_equal(X, X0)                            # pure
+
+
+# positions of the 26 compact entries as (row dof, cell offset index k in the mask order, column dof)
+_COMPACT = [(0, 0, 2), (0, 2, 1), (0, 3, 1), (0, 3, 2),
+            (1, 0, 1), (1, 0, 2), (1, 1, 2), (1, 2, 1), (1, 3, 0), (1, 3, 1), (1, 3, 2), (1, 4, 0), (1, 4, 1),
+            (1, 4, 2), (1, 6, 1),
+            (2, 0, 2), (2, 2, 1), (2, 2, 2), (2, 3, 0), (2, 3, 1), (2, 3, 2), (2, 4, 2), (2, 5, 1), (2, 6, 0),
+            (2, 6, 1), (2, 6, 2)]
+
+
+@pytest.mark.parametrize("nx,ny", [(9, 8), (64, 64), (100, 100), (300, 70)])
+def test_compact_jacobian_and_spmv(cuda, nx, ny):
+    """the solver's 26-entry layout holds exactly the CSR numbers; every other mask entry is 0"""
+    from oracle import ldc_oracle as orc
+    import scipy.sparse as sp
+    torch, native = cuda['torch'], cuda['native']
+    g, X = synthetic_case(nx, ny, seed=3 * nx + ny)
+    N = nx * ny
+    indptr, indices = orc.jacobian_mask_arrays(nx, ny, 3)
+    J_ref = orc.fd_jacobian(X, g, mask=(indptr, indices))
+    A = sp.csr_matrix((J_ref, indices, indptr), shape=(3 * N, 3 * N))
+    Xd = torch.from_numpy(X).cuda()
+    Ud = torch.from_numpy(g.ns_x_mesh.phi_old).cuda()
+    Vd = torch.from_numpy(g.ns_y_mesh.phi_old).cuda()
+    Jc = torch.full((26 * N,), np.nan, dtype=torch.float64, device='cuda')
+    grid = native.grid_from_graph(g)
+    native.check(native.lib().ldc_fd_jacobian_compact(grid, native.ptr(Xd), native.ptr(Ud), native.ptr(Vd),
+                                                      native.ptr(Jc), native.current_stream()))
+    Jc = Jc.cpu().numpy().reshape(26, N)
+    offs = [-nx, -nx + 1, -1, 0, 1, nx - 1, nx]
+    rebuilt = sp.lil_matrix((3 * N, 3 * N))
+    cells = np.arange(N)
+    for k, (d, o, e) in enumerate(_COMPACT):
+        cc = cells + offs[o]
+        ok = (cc >= 0) & (cc < N)
+        assert np.all(Jc[k][~ok] == 0.0)
+        rows, cols = 3 * cells[ok] + d, 3 * cc[ok] + e
+        assert np.array_equal(Jc[k][ok], np.asarray(A[rows, cols]).ravel()), k
+        rebuilt[rows, cols] = Jc[k][ok]
+    assert (abs(rebuilt.tocsr() - A)).max() == 0.0          # nothing outside the 26 entries
+    x = np.random.default_rng(1).standard_normal(3 * N)
+    xd = torch.from_numpy(x).cuda()
+    y = torch.empty_like(xd)
+    native.check(native.lib().ldc_spmv_compact(grid, native.ptr(torch.from_numpy(Jc.ravel()).cuda()), native.ptr(xd),
+                                               native.ptr(y), native.current_stream()))
+    y_ref = A @ x
+    assert np.abs(y.cpu().numpy() - y_ref).max() <= 1e-13 * np.abs(y_ref).max()
