@@ -125,7 +125,7 @@ typedef struct ldc_solver_options {
     int32_t mg_min_size;                      /* do not coarsen below this many cells per side */
     int32_t residual_variant;                 /* as in ldc_residual */
     int32_t gmres_refine;                     /* 1: second Gram-Schmidt pass (CGS2); 0: PETSc's default (never) */
-    int32_t reserved;
+    int32_t use_cuda_graphs;                  /* 1: replay each Krylov iteration as one CUDA graph */
     double pc_omega_u, pc_omega_p;            /* damping of the cell-block relaxation */
 } ldc_solver_options;
 

@@ -10,7 +10,7 @@ from conftest import make_graph
 
 pytestmark = pytest.mark.gpu
 
-TIGHT = dict(snes_rtol=1e-13, snes_atol=1e-9, snes_stol=1e-15, ksp_rtol=1e-8, snes_max_it=30)
+TIGHT = dict(snes_rtol=1e-13, snes_atol=1e-9, snes_stol=1e-15, ksp_rtol=1e-8, snes_max_it=30, gmres_refine=1)
 
 
 def _rel(a, b):
