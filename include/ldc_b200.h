@@ -116,7 +116,7 @@ typedef struct ldc_solver_options {
     int32_t snes_max_it;                      /* 50 */
     int32_t snes_max_funcs;                   /* 10000 (PETSc default) */
     double ksp_rtol, ksp_atol, ksp_dtol;      /* 1e-5, 1e-50, 1e5 (PETSc KSP defaults) */
-    int32_t ksp_max_it;                       /* 500 (PETSc: 10000 with ILU) */
+    int32_t ksp_max_it;                       /* 150 (PETSc: 10000 with ILU) */
     int32_t gmres_restart;                    /* 30 */
     int32_t pc_type;                          /* LDC_PC_* */
     int32_t pc_sweeps;                        /* relaxation sweeps before and after each coarse correction */
@@ -158,6 +158,9 @@ LDC_API int ldc_solver_set_bc(ldc_solver *s, const double *bc_host);
 /* device-to-device copies of the whole interleaved state */
 LDC_API int ldc_solver_set_state(ldc_solver *s, const double *X_dev, void *stream);
 LDC_API int ldc_solver_get_state(ldc_solver *s, double *X_dev, void *stream);
+/* out3 = {Krylov iterations executed in lock step, sum over cavities of their own Krylov
+ * iterations, Newton iterations (Jacobian builds) executed} since creation */
+LDC_API int ldc_solver_counters(ldc_solver *s, int64_t *out3);
 /* number of multigrid levels the solver built */
 LDC_API int ldc_solver_num_levels(ldc_solver *s);
 /* Building block exposed for the parity tests: assemble the FD Jacobian (and its multigrid

@@ -76,6 +76,7 @@ SYMBOLS = {
     'ldc_solver_set_state': (ctypes.c_int, [_vp, _vp, _vp]),
     'ldc_solver_get_state': (ctypes.c_int, [_vp, _vp, _vp]),
     'ldc_solver_num_levels': (ctypes.c_int, [_vp]),
+    'ldc_solver_counters': (ctypes.c_int, [_vp, ctypes.POINTER(_i64)]),
     'ldc_solver_linear_solve': (ctypes.c_int, [_vp, _vp, _vp, c_int32_p, c_int32_p, c_double_p, _vp]),
     'ldc_solver_step': (ctypes.c_int, [_vp, c_int32_p, ctypes.POINTER(LdcNewtonReport), c_double_p, _vp]),
 }

@@ -157,6 +157,7 @@ struct ldc_solver {
     int32_t *mask_host;
     std::vector<double> dt_host, bc_host;
     long total_linear_its;
+    long lockstep_krylov_its, lockstep_newton_its, kernel_launch_estimate;
     // private stream (graph capture is illegal on the legacy default stream) and one CUDA graph per
     // position k in the restart cycle: every kernel argument of Krylov iteration k is fixed for the
     // life of the solver (basis vectors V_k/Z_k, level buffers, device scalars), so the ~200 small
@@ -211,7 +212,8 @@ extern "C" void ldc_solver_default_options(ldc_solver_options *o)
     o->ksp_rtol = 1e-5;     // PETSc KSP defaults
     o->ksp_atol = 1e-50;
     o->ksp_dtol = 1e5;
-    o->ksp_max_it = 500;    // PETSc: 10000 (ILU); a multigrid-preconditioned solve that needs more has failed
+    o->ksp_max_it = 150;    // PETSc: 10000 (ILU).  A multigrid-preconditioned solve that needs more is a
+                            // Newton step about to diverge: failing fast (-> dt halving) is 1.4-2x cheaper
     o->gmres_restart = 30;
     o->gmres_refine = 0;    // PETSc's default (classical Gram-Schmidt, never refine)
     o->use_cuda_graphs = 1;
@@ -258,6 +260,7 @@ extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *op
     s->n = 3 * s->N;
     s->nnz = ldc_mask_nnz(g->nx, g->ny, 3);
     s->total_linear_its = 0;
+    s->lockstep_krylov_its = s->lockstep_newton_its = s->kernel_launch_estimate = 0;
     s->stream = nullptr;
     s->ev_in = nullptr;
     s->use_graphs = (o.use_cuda_graphs != 0) && (getenv("LDC_NO_GRAPHS") == nullptr);
@@ -371,6 +374,15 @@ extern "C" double *ldc_solver_state_dev(ldc_solver *s) { return s ? s->X : nullp
 
 extern "C" int ldc_solver_num_levels(ldc_solver *s) { return s ? (int)s->levels.size() : 0; }
 
+extern "C" int ldc_solver_counters(ldc_solver *s, int64_t *out3)
+{
+    LDC_REQUIRE(s && out3, "ldc_solver_counters: null argument");
+    out3[0] = s->lockstep_krylov_its;   // Krylov iterations executed (a batch advances in lock step)
+    out3[1] = s->total_linear_its;      // sum over cavities of their own Krylov iterations
+    out3[2] = s->lockstep_newton_its;   // Newton iterations executed (Jacobian builds)
+    return LDC_OK;
+}
+
 extern "C" int ldc_solver_set_state(ldc_solver *s, const double *X_dev, void *stream)
 {
     LDC_REQUIRE(s && X_dev, "ldc_solver_set_state: null argument");
@@ -441,7 +453,14 @@ static int vcycle(ldc_solver *s, size_t l, const double *b, double *x, const int
     const double ou = s->opt.pc_omega_u, op = s->opt.pc_omega_p;
     const int B = s->batch;
     if (l + 1 == s->levels.size()) {
-        const int sweeps = (s->levels.size() == 1) ? s->opt.pc_sweeps : s->opt.mg_coarse_sweeps;
+        // the coarsest grid is relaxed until it is (roughly) solved: a few sweeps on a 4x4 grid,
+        // ~2 per cell row when the grid could not be coarsened further (e.g. 100 -> 50 -> 25)
+        int sweeps = s->opt.pc_sweeps;
+        if (s->levels.size() > 1) {
+            sweeps = s->opt.mg_coarse_sweeps;
+            const int side = L.nx > L.ny ? L.nx : L.ny;
+            if (sweeps < 2 * side) sweeps = 2 * side;
+        }
         for (int k = 0; k < sweeps; ++k) TRY(mg_vanka_sweep(L, b, x, k == 0, ou, op, B, run, st));
         if (s->levels.size() > 1) TRY(mg_remove_mean_pressure(L, x, B, run, nullptr, nullptr, st));
         return LDC_OK;
@@ -567,6 +586,7 @@ static int fgmres(ldc_solver *s, const double *rhs, double *y, std::vector<int32
         int k = 0;
         for (; k < m && any(run); ++k) {
             TRY(krylov_iteration(s, k, st));
+            s->lockstep_krylov_its += 1;
             LDC_CUDA(cudaMemcpyAsync(s->res_host, s->ks.res, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
             LDC_CUDA(cudaStreamSynchronize(st));
             std::vector<int32_t> fin(B, 0);
@@ -684,6 +704,7 @@ extern "C" int ldc_solver_step(ldc_solver *s, const int32_t *active_host, ldc_ne
 
     for (int it = 0; it < o.snes_max_it && any(run); ++it) {
         TRY(build_hierarchy(s, st));
+        s->lockstep_newton_its += 1;
         std::vector<int32_t> kreason, kits;
         std::vector<double> krel;
         TRY(fgmres(s, s->F, s->Y, run, fnorm, kreason, kits, krel, st));

@@ -152,6 +152,11 @@ class CudaEnsembleSolver(object):
                 self.krylov_iterations[b] += reports[b].linear_iterations
         return reasons, np.array([du[b] for b in range(B)])
 
+    def counters(self):
+        out = (ctypes.c_int64 * 3)()
+        self._native.check(self._native.lib().ldc_solver_counters(self._handle, out), 'counters')
+        return dict(lockstep_krylov=int(out[0]), krylov_sum=int(out[1]), lockstep_newton=int(out[2]))
+
     def fields(self):
         """(U, V, P) as numpy arrays of shape (batch, mesh size)"""
         _native, lib = self._native, self._native.lib()
@@ -199,6 +204,7 @@ def run_ensemble(graphs, final_time=None, minimum_dt=1e-6, adaptative_dt=True, m
         solver = CudaEnsembleSolver(local, **solver_options)
         ts = solver.run(final_time, minimum_dt, adaptative_dt, max_steps)
         fields = solver.fields()
+        run_ensemble.last_counters = dict(solver.counters(), sweeps=int(ts.steps.max() + ts.retries.max()))
         for b in range(len(local)):
             summaries.append(dict(index=mine.start + b, bc=float(local[b].bc), status=int(ts.status[b]),
                                   t=float(ts.t[b]), dt=float(ts.dt[b]), steps=int(ts.steps[b]),

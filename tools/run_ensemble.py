@@ -53,7 +53,7 @@ def main():
                               retries_total=int(sum(s['retries'] for s in summ)),
                               newton_total=int(sum(s['newton'] for s in summ)),
                               krylov_total=int(sum(s['krylov'] for s in summ)),
-                              cavities_per_s=round(K / sec, 2))))
+                              cavities_per_s=round(K / sec, 2), rank0_counters=getattr(run_ensemble, 'last_counters', None))))
     if world > 1:
         dist.destroy_process_group()
 
