@@ -204,7 +204,8 @@ def run_ensemble(graphs, final_time=None, minimum_dt=1e-6, adaptative_dt=True, m
         solver = CudaEnsembleSolver(local, **solver_options)
         ts = solver.run(final_time, minimum_dt, adaptative_dt, max_steps)
         fields = solver.fields()
-        run_ensemble.last_counters = dict(solver.counters(), sweeps=int(ts.steps.max() + ts.retries.max()))
+        counters = solver.counters() if hasattr(solver, 'counters') else {}
+        run_ensemble.last_counters = dict(counters, sweeps=int((ts.steps + ts.retries).max()))
         for b in range(len(local)):
             summaries.append(dict(index=mine.start + b, bc=float(local[b].bc), status=int(ts.status[b]),
                                   t=float(ts.t[b]), dt=float(ts.dt[b]), steps=int(ts.steps[b]),
