@@ -83,7 +83,7 @@ assert all(s["retries"] == 1 and s["status"] == ensemble.STEADY for s in summ)
 owners = [s["rank"] for s in summ]
 assert owners == [0, 0, 0, 0, 1, 1, 1], owners
 dist.barrier(); dist.destroy_process_group()
-print("rank", rank, "ok")
+sys.stdout.write("rank%dok\n" % rank); sys.stdout.flush()
 '''
 
 
@@ -97,7 +97,7 @@ def test_distributed_sharding_gloo_world2(tmp_path):
                         '--master-addr', '127.0.0.1', '--master-port', str(port), str(script)],
                        env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert 'rank 0 ok' in r.stdout and 'rank 1 ok' in r.stdout
+    assert 'rank0ok' in r.stdout and 'rank1ok' in r.stdout
 
 
 @pytest.mark.gpu
