@@ -104,6 +104,19 @@ LDC_API int ldc_spmv_mask(const ldc_grid *g, const double *values_dev, const dou
 LDC_API int ldc_spmv_csr(int64_t n_rows, const int32_t *indptr_dev, const int32_t *indices_dev,
                  const double *values_dev, const double *x_dev, double *y_dev, void *stream);
 
+/* ---- transport hooks for the row-strip decomposition.  The compute library never
+ * links a communication library: a distributed solver calls these two functions, implemented by
+ * libldc_b200_comm.so over NCCL (include/ldc_b200_comm.h) or by anything else. */
+typedef struct ldc_comm_ops {
+    void *ctx;
+    int32_t rank, nranks;
+    /* one-row halo exchange of a [ghost | row_count owned rows | ghost] buffer, see ldc_b200_comm.h */
+    int (*halo_exchange)(void *ctx, double *first_owned_row_dev, int64_t row_doubles,
+                         int64_t row_count, void *stream);
+    /* in-place all-reduce of device doubles; op 0 = sum, 1 = max */
+    int (*allreduce)(void *ctx, double *buf_dev, int64_t count, int32_t op, void *stream);
+} ldc_comm_ops;
+
 /* ---- device-resident Newton-Krylov solve of one pseudo-time step and the time stepper.
  * Replaces PetscSolverWrapper.solve/_setup_snes/_setup_options
  * (nonlinear_solver/petsc_solver_wrapper.py:35-145) and the loop of

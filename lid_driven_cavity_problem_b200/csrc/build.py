@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ['common.cu', 'residual.cu', 'pack.cu', 'jacobian.cu', 'spmv.cu', 'vector_ops.cu',
            'precond.cu', 'solver.cu']
 LIB = os.path.join(HERE, 'libldc_b200.so')
+COMM_LIB = os.path.join(HERE, 'libldc_b200_comm.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC,-fvisibility=hidden', '--expt-relaxed-constexpr',
@@ -60,7 +61,42 @@ def build(force=False, verbose=False):
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError('link failed')
+    build_comm(force=force)
     return LIB
+
+
+def _nccl_paths():
+    import importlib.util
+    spec = importlib.util.find_spec('nvidia.nccl')
+    if spec is not None and spec.submodule_search_locations:
+        root = list(spec.submodule_search_locations)[0]
+        inc, lib = os.path.join(root, 'include'), os.path.join(root, 'lib')
+        if os.path.exists(os.path.join(inc, 'nccl.h')) and os.path.exists(os.path.join(lib, 'libnccl.so.2')):
+            return inc, lib
+    if os.path.exists('/usr/include/nccl.h'):
+        return '/usr/include', '/usr/lib/x86_64-linux-gnu'
+    return None, None
+
+
+def build_comm(force=False):
+    """libldc_b200_comm.so: the NCCL transport (links the same libnccl.so.2 torch loads)."""
+    src = os.path.join(HERE, 'comm.cu')
+    if not os.path.exists(src):
+        return None
+    inc, lib = _nccl_paths()
+    if inc is None:
+        sys.stderr.write('nccl.h not found: libldc_b200_comm.so not built\n')
+        return None
+    deps = [src, os.path.join(HERE, '..', '..', 'include', 'ldc_b200_comm.h'),
+            os.path.join(HERE, '..', '..', 'include', 'ldc_b200.h')]
+    if force or _stale(COMM_LIB, deps):
+        cmd = [NVCC] + FLAGS + ['-shared', '-I', inc, src, '-o', COMM_LIB, '-L', lib, '-l:libnccl.so.2',
+                                '-Xlinker', '-rpath,' + lib]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError('comm library build failed')
+    return COMM_LIB
 
 
 if __name__ == '__main__':

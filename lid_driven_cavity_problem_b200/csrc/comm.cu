@@ -1,0 +1,119 @@
+// NCCL transport of the row-strip decomposition (libldc_b200_comm.so, see
+// include/ldc_b200_comm.h).  Halo rows are latency-bound messages (3*nx doubles = 96 KiB at
+// nx = 4096): both directions go into ONE NCCL group so they share a launch, and the calls are
+// made from C (a few microseconds of host time) rather than through a Python collective layer,
+// which matters because the kernels they feed run for only tens of microseconds.
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ldc_b200_comm.h"
+
+struct ldc_comm {
+    ncclComm_t comm;
+    int rank, nranks;
+    ldc_comm_ops ops;
+};
+
+static thread_local char g_comm_error[512] = "";
+
+static int comm_fail(const char *what, const char *detail)
+{
+    snprintf(g_comm_error, sizeof(g_comm_error), "%s: %s", what, detail);
+    return LDC_ERR_CUDA;
+}
+
+#define LDC_NCCL(call)                                                       \
+    do {                                                                     \
+        ncclResult_t r__ = (call);                                           \
+        if (r__ != ncclSuccess) return comm_fail(#call, ncclGetErrorString(r__)); \
+    } while (0)
+
+static int halo_cb(void *ctx, double *first, int64_t row_doubles, int64_t row_count, void *stream)
+{
+    return ldc_comm_halo_exchange((ldc_comm *)ctx, first, row_doubles, row_count, stream);
+}
+
+static int allreduce_cb(void *ctx, double *buf, int64_t count, int32_t op, void *stream)
+{
+    return ldc_comm_allreduce((ldc_comm *)ctx, buf, count, op, stream);
+}
+
+extern "C" const char *ldc_comm_last_error(void) { return g_comm_error; }
+
+extern "C" int ldc_comm_unique_id(void *id_out)
+{
+    static_assert(sizeof(ncclUniqueId) <= LDC_COMM_ID_BYTES, "ncclUniqueId larger than expected");
+    if (!id_out) return comm_fail("ldc_comm_unique_id", "null argument");
+    ncclUniqueId id;
+    LDC_NCCL(ncclGetUniqueId(&id));
+    memset(id_out, 0, LDC_COMM_ID_BYTES);
+    memcpy(id_out, &id, sizeof(id));
+    return LDC_OK;
+}
+
+extern "C" int ldc_comm_create(const void *id_bytes, int32_t nranks, int32_t rank, ldc_comm **out)
+{
+    if (!id_bytes || !out || nranks < 1 || rank < 0 || rank >= nranks)
+        return comm_fail("ldc_comm_create", "bad arguments");
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof(id));
+    ldc_comm *c = new ldc_comm();
+    c->rank = rank;
+    c->nranks = nranks;
+    ncclResult_t r = ncclCommInitRank(&c->comm, nranks, id, rank);
+    if (r != ncclSuccess) {
+        delete c;
+        return comm_fail("ncclCommInitRank", ncclGetErrorString(r));
+    }
+    c->ops.ctx = c;
+    c->ops.rank = rank;
+    c->ops.nranks = nranks;
+    c->ops.halo_exchange = halo_cb;
+    c->ops.allreduce = allreduce_cb;
+    *out = c;
+    return LDC_OK;
+}
+
+extern "C" void ldc_comm_destroy(ldc_comm *c)
+{
+    if (!c) return;
+    ncclCommDestroy(c->comm);
+    delete c;
+}
+
+extern "C" const ldc_comm_ops *ldc_comm_get_ops(ldc_comm *c) { return c ? &c->ops : nullptr; }
+
+extern "C" int ldc_comm_halo_exchange(ldc_comm *c, double *first, int64_t row_doubles,
+                                      int64_t row_count, void *stream)
+{
+    if (!c || !first || row_doubles <= 0 || row_count <= 0)
+        return comm_fail("ldc_comm_halo_exchange", "bad arguments");
+    if (c->nranks == 1) return LDC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    double *ghost_below = first - row_doubles;
+    double *last = first + (row_count - 1) * row_doubles;
+    double *ghost_above = first + row_count * row_doubles;
+    LDC_NCCL(ncclGroupStart());
+    if (c->rank > 0) {
+        LDC_NCCL(ncclSend(first, (size_t)row_doubles, ncclDouble, c->rank - 1, c->comm, st));
+        LDC_NCCL(ncclRecv(ghost_below, (size_t)row_doubles, ncclDouble, c->rank - 1, c->comm, st));
+    }
+    if (c->rank < c->nranks - 1) {
+        LDC_NCCL(ncclSend(last, (size_t)row_doubles, ncclDouble, c->rank + 1, c->comm, st));
+        LDC_NCCL(ncclRecv(ghost_above, (size_t)row_doubles, ncclDouble, c->rank + 1, c->comm, st));
+    }
+    LDC_NCCL(ncclGroupEnd());
+    return LDC_OK;
+}
+
+extern "C" int ldc_comm_allreduce(ldc_comm *c, double *buf, int64_t count, int32_t op, void *stream)
+{
+    if (!c || !buf || count <= 0) return comm_fail("ldc_comm_allreduce", "bad arguments");
+    if (c->nranks == 1) return LDC_OK;
+    LDC_NCCL(ncclAllReduce(buf, buf, (size_t)count, ncclDouble, op == 1 ? ncclMax : ncclSum, c->comm,
+                           (cudaStream_t)stream));
+    return LDC_OK;
+}

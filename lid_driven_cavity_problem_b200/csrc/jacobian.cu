@@ -85,16 +85,18 @@ fd_jacobian_kernel(const ldc_grid g, const double *__restrict__ X,
 {
     __shared__ double stage[CSR ? kFdCells * 63 : 1];
 
+    // Row strips (compact output only): cells are the strip's own, c = i + nx*jl with jl the local
+    // row; X points at the first owned row with ghost rows around it (include/ldc_b200.h).
     const int inst = blockIdx.y;
     const int nx = g.nx, ny = g.ny;
-    const long N = (long)nx * ny;
+    const long N = (long)nx * g.row_count;
     X += inst * 3 * N;
-    U_old += inst * (long)(nx - 1) * ny;
-    V_old += inst * (long)nx * (ny - 1);
+    U_old += inst * (long)(nx - 1) * g.row_count;
+    V_old += inst * (long)nx * (ny - 1);   // batch > 1 implies the full grid
     if (CSR) values += inst * nnz;
     if (COMPACT) compact += inst * 26 * N;
     const Phys p = make_phys(g, inst);
-    const GridView gv{X, nx, ny, 0};
+    const GridView gv{X, nx, ny, g.row_begin};
     const MaskGeom m{nx, N};
 
     const long c0 = (long)blockIdx.x * kFdCells;
@@ -109,7 +111,8 @@ fd_jacobian_kernel(const ldc_grid g, const double *__restrict__ X,
 
     const long c = c0 + threadIdx.x;
     if (c < c1) {
-        const int j = (int)(c / nx), i = (int)(c - (long)j * nx);
+        const int jl = (int)(c / nx), i = (int)(c - (long)jl * nx);
+        const int j = g.row_begin + jl;   // grid row
         const int lo = m.lo_missing(c), cnt = m.count(c);
         double *row0 = stage + (CSR ? (m.row_start(c, 0) - chunk_base) : 0);
         double *row1 = row0 + (CSR ? 3 * cnt : 0);
@@ -149,7 +152,7 @@ fd_jacobian_kernel(const ldc_grid g, const double *__restrict__ X,
         // ---- x-momentum row of U[i,j] (or the dummy row F = X)
         if (E) {
             XmomIn s;
-            gather_xmom(gv, i, j, p.bc, __ldg(U_old + i + (long)(nx - 1) * j), s);
+            gather_xmom(gv, i, j, p.bc, __ldg(U_old + i + (long)(nx - 1) * jl), s);
             const double f0 = xmom_row<POW2>(s, p);
             const bool E2 = i < nx - 2;  // U[i+1,j] is a real unknown
             double v;
@@ -208,9 +211,11 @@ fd_jacobian_kernel(const ldc_grid g, const double *__restrict__ X,
 int fd_jacobian_launch(const ldc_grid *g, const double *X, const double *U_old, const double *V_old,
                        double *csr_values, double *compact, cudaStream_t st)
 {
-    const long N = (long)g->nx * g->ny;
+    const long N = (long)g->nx * g->row_count;
     const long nnz = ldc_mask_nnz(g->nx, g->ny, 3);
     dim3 grid((unsigned)((N + kFdCells - 1) / kFdCells), g->batch);
+    const bool full = g->row_begin == 0 && g->row_count == g->ny;
+    LDC_REQUIRE(full || csr_values == nullptr, "the CSR(mask) output needs the full grid; strips use the compact layout");
     const bool pow2 = is_pow2_double(g->dx) && is_pow2_double(g->dy);
 #define LDC_FD_LAUNCH(P2, C1, C2) \
     fd_jacobian_kernel<P2, C1, C2><<<grid, kFdCells, 0, st>>>(*g, X, U_old, V_old, csr_values, nnz, compact)
@@ -259,7 +264,7 @@ extern "C" int ldc_fd_jacobian(const ldc_grid *g, const double *X_dev, const dou
 extern "C" int ldc_fd_jacobian_compact(const ldc_grid *g, const double *X_dev, const double *U_old_dev,
                                        const double *V_old_dev, double *compact_dev, void *stream)
 {
-    if (int rc = validate_grid(g, true)) return rc;
+    if (int rc = validate_grid(g, false)) return rc;
     LDC_REQUIRE(X_dev && U_old_dev && V_old_dev && compact_dev, "ldc_fd_jacobian_compact: null device pointer");
     return fd_jacobian_launch(g, X_dev, U_old_dev, V_old_dev, nullptr, compact_dev, (cudaStream_t)stream);
 }

@@ -55,8 +55,10 @@ int fd_jacobian_launch(const ldc_grid *g, const double *X, const double *U_old, 
 int spmv_mask_launch(int nx, int ny, int batch, const double *values, const double *x,
                      const double *b, double *y, const int32_t *run, cudaStream_t s);
 // same on the compact layout Jc[26][N] (see jacobian.cu)
+// ny = rows of the block of cells; ghost_lo/ghost_hi: x carries valid halo rows below/above
 int spmv_compact_launch(int nx, int ny, int batch, const double *Jc, const double *x,
-                        const double *b, double *y, const int32_t *run, cudaStream_t s);
+                        const double *b, double *y, const int32_t *run, cudaStream_t s,
+                        bool ghost_lo = false, bool ghost_hi = false);
 
 // ---- precond.cu ----------------------------------------------------------------------------
 struct MgLevel {

@@ -131,8 +131,11 @@ static constexpr int kCmpLo = 0, kCmpMid = 3 * 257, kCmpHi = 3 * (257 + 258), kC
 __global__ void __launch_bounds__(kCmpCells)
 spmv_compact_kernel(int nx, int ny, const double *__restrict__ Jc, const double *__restrict__ x,
                     const double *__restrict__ rhs, double *__restrict__ y,
-                    const int32_t *__restrict__ run)
+                    const int32_t *__restrict__ run, int ghost_lo, int ghost_hi)
 {
+    // ny = rows of this block of cells (a whole cavity or a row strip).  For a strip, x points at
+    // the first owned row and ghost_lo / ghost_hi say whether the row below / above it holds valid
+    // halo data; without them the product is the strip's diagonal block (block-Jacobi).
     if (run && !run[blockIdx.y]) return;
     __shared__ double xs[kCmpXs];
     __shared__ double ys[3 * kCmpCells];
@@ -145,6 +148,7 @@ spmv_compact_kernel(int nx, int ny, const double *__restrict__ Jc, const double 
     const long c0 = (long)blockIdx.x * kCmpCells;
     const int tid = threadIdx.x;
     const long c = c0 + tid;
+    const long cell_lo = ghost_lo ? -(long)nx : 0, cell_hi = N + (ghost_hi ? nx : 0);
 
     // coefficient loads first: they are independent of the staging below
     double J[26];
@@ -161,7 +165,7 @@ spmv_compact_kernel(int nx, int ny, const double *__restrict__ Jc, const double 
         if (t < kCmpMid) { cell = c0 - nx + t / 3; e = t % 3; }
         else if (t < kCmpHi) { cell = c0 - 1 + (t - kCmpMid) / 3; e = (t - kCmpMid) % 3; }
         else { cell = c0 + nx - 1 + (t - kCmpHi) / 3; e = (t - kCmpHi) % 3; }
-        xs[t] = (cell >= 0 && cell < N) ? __ldg(x + 3 * cell + e) : 0.0;
+        xs[t] = (cell >= cell_lo && cell < cell_hi) ? __ldg(x + 3 * cell + e) : 0.0;
     }
     __syncthreads();
     {
@@ -257,11 +261,12 @@ int spmv_mask_launch(int nx, int ny, int batch, const double *values, const doub
     return LDC_OK;
 }
 int spmv_compact_launch(int nx, int ny, int batch, const double *Jc, const double *x,
-                        const double *b, double *y, const int32_t *run, cudaStream_t s)
+                        const double *b, double *y, const int32_t *run, cudaStream_t s,
+                        bool ghost_lo, bool ghost_hi)
 {
     const long N = (long)nx * ny;
     dim3 grid((unsigned)((N + kCmpCells - 1) / kCmpCells), batch);
-    spmv_compact_kernel<<<grid, kCmpCells, 0, s>>>(nx, ny, Jc, x, b, y, run);
+    spmv_compact_kernel<<<grid, kCmpCells, 0, s>>>(nx, ny, Jc, x, b, y, run, ghost_lo ? 1 : 0, ghost_hi ? 1 : 0);
     LDC_CHECK_LAUNCH();
     return LDC_OK;
 }
@@ -272,10 +277,11 @@ using namespace ldc;
 extern "C" int ldc_spmv_compact(const ldc_grid *g, const double *compact_dev, const double *x_dev,
                                 double *y_dev, void *stream)
 {
-    if (int rc = validate_grid(g, true)) return rc;
+    if (int rc = validate_grid(g, false)) return rc;
     LDC_REQUIRE(compact_dev && x_dev && y_dev && x_dev != y_dev, "ldc_spmv_compact: bad device pointers");
-    return spmv_compact_launch(g->nx, g->ny, g->batch, compact_dev, x_dev, nullptr, y_dev, nullptr,
-                               (cudaStream_t)stream);
+    // row strip: x_dev points at the first owned row, halo rows (if the strip has neighbours) around it
+    return spmv_compact_launch(g->nx, g->row_count, g->batch, compact_dev, x_dev, nullptr, y_dev, nullptr,
+                               (cudaStream_t)stream, g->row_begin > 0, g->row_begin + g->row_count < g->ny);
 }
 
 extern "C" int ldc_spmv_mask(const ldc_grid *g, const double *values_dev, const double *x_dev,

@@ -253,3 +253,44 @@ def test_compact_jacobian_and_spmv(cuda, nx, ny):
                                                native.ptr(y), native.current_stream()))
     y_ref = A @ x
     assert np.abs(y.cpu().numpy() - y_ref).max() <= 1e-13 * np.abs(y_ref).max()
+
+
+def test_compact_jacobian_and_spmv_row_strips(cuda):
+    """row-strip decomposition of the Jacobian assembly and the SpMV: every strip (with its halo
+    rows of X / x) reproduces its slice of the full-grid result bit for bit"""
+    torch, native = cuda['torch'], cuda['native']
+    lib = native.lib()
+    nx, ny = 64, 50
+    g, X = synthetic_case(nx, ny)
+    N = nx * ny
+    st = native.current_stream()
+    Xd = torch.from_numpy(X).cuda()
+    Ud = torch.from_numpy(g.ns_x_mesh.phi_old).cuda()
+    Vd = torch.from_numpy(g.ns_y_mesh.phi_old).cuda()
+    Jfull = torch.empty(26 * N, dtype=torch.float64, device='cuda')
+    grid = native.grid_from_graph(g)
+    native.check(lib.ldc_fd_jacobian_compact(grid, native.ptr(Xd), native.ptr(Ud), native.ptr(Vd), native.ptr(Jfull), st))
+    x = np.random.default_rng(2).standard_normal(3 * N)
+    xd = torch.from_numpy(x).cuda()
+    yfull = torch.empty_like(xd)
+    native.check(lib.ldc_spmv_compact(grid, native.ptr(Jfull), native.ptr(xd), native.ptr(yfull), st))
+    Jfull = Jfull.cpu().numpy().reshape(26, ny, nx)
+    yfull = yfull.cpu().numpy()
+    U_old = g.ns_x_mesh.phi_old.reshape(ny, nx - 1)
+    V_old = g.ns_y_mesh.phi_old.reshape(ny - 1, nx)
+    bounds = [0, 13, 14, 32, 50]
+    for j0, j1 in zip(bounds[:-1], bounds[1:]):
+        lo, hi = max(j0 - 1, 0), min(j1 + 1, ny)
+        rows = j1 - j0
+        Xl = torch.from_numpy(X[3 * nx * lo:3 * nx * hi].copy()).cuda()
+        xl = torch.from_numpy(x[3 * nx * lo:3 * nx * hi].copy()).cuda()
+        Ul = torch.from_numpy(U_old[j0:j1].copy().ravel()).cuda()
+        Vl = torch.from_numpy(np.r_[V_old[j0:min(j1, ny - 1)].ravel(), np.zeros(nx)]).cuda()
+        sg = native.grid_from_graph(g, row_begin=j0, row_count=rows)
+        off = 8 * 3 * nx * (j0 - lo)
+        Jl = torch.full((26 * nx * rows,), np.nan, dtype=torch.float64, device='cuda')
+        native.check(lib.ldc_fd_jacobian_compact(sg, Xl.data_ptr() + off, native.ptr(Ul), native.ptr(Vl), native.ptr(Jl), st))
+        assert np.array_equal(Jl.cpu().numpy().reshape(26, rows, nx), Jfull[:, j0:j1, :]), (j0, j1)
+        yl = torch.empty(3 * nx * rows, dtype=torch.float64, device='cuda')
+        native.check(lib.ldc_spmv_compact(sg, native.ptr(Jl), xl.data_ptr() + off, native.ptr(yl), st))
+        assert np.array_equal(yl.cpu().numpy(), yfull[3 * nx * j0:3 * nx * j1]), (j0, j1)

@@ -1,8 +1,8 @@
 """Reynolds ensemble (BASELINE config 4): `--count` independent n x n cavities, Re log-spaced
 100..10000, batch-sharded over the visible GPUs (launch with torchrun for N > 1).
 
-    python tools/run_ensemble.py --count 512 --n 64
-    python -m torch.distributed.run --nproc-per-node 8 tools/run_ensemble.py --count 512 --n 64
+    python tools/run_ensemble.py --count 512 --grid 64
+    python -m torch.distributed.run --nproc-per-node 8 tools/run_ensemble.py --count 512 --grid 64
 """
 import argparse
 import json
@@ -19,7 +19,7 @@ sys.path.insert(0, REPO)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--count', type=int, default=512)
-    ap.add_argument('--n', type=int, default=64)
+    ap.add_argument('--grid', type=int, default=64)
     ap.add_argument('--re-min', type=float, default=100.0)
     ap.add_argument('--re-max', type=float, default=10000.0)
     ap.add_argument('--max-steps', type=int, default=None)
@@ -35,7 +35,7 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     K = args.count
     res = args.re_min * (args.re_max / args.re_min) ** (np.arange(K) / max(K - 1, 1))
-    graphs = [Graph(1.0, 1.0, args.n, args.n, 1e-2, 1.0, 1.0, float(r)) for r in res]
+    graphs = [Graph(1.0, 1.0, args.grid, args.grid, 1e-2, 1.0, 1.0, float(r)) for r in res]
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -47,7 +47,7 @@ def main():
     sec = time.time() - t0
     if int(os.environ.get('RANK', '0')) == 0:
         st = np.array([s['status'] for s in summ])
-        print(json.dumps(dict(cavities=K, grid='%dx%d' % (args.n, args.n), gpus=world, seconds=round(sec, 3),
+        print(json.dumps(dict(cavities=K, grid='%dx%d' % (args.grid, args.grid), gpus=world, seconds=round(sec, 3),
                               steady=int((st == STEADY).sum()), failed=int((st == FAILED).sum()),
                               steps_total=int(sum(s['steps'] for s in summ)),
                               retries_total=int(sum(s['retries'] for s in summ)),
