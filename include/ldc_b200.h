@@ -171,6 +171,12 @@ LDC_API int ldc_solver_set_bc(ldc_solver *s, const double *bc_host);
 /* device-to-device copies of the whole interleaved state */
 LDC_API int ldc_solver_set_state(ldc_solver *s, const double *X_dev, void *stream);
 LDC_API int ldc_solver_get_state(ldc_solver *s, double *X_dev, void *stream);
+/* Row strips: a solver created on a grid with row_begin/row_count holds that strip only (state,
+ * Krylov basis, Jacobian rows); with a transport attached, halo rows of the state and of every
+ * SpMV input are exchanged with the neighbouring strips and every norm / Gram-Schmidt coefficient
+ * is all-reduced, so all ranks take identical decisions.  The preconditioner is block-Jacobi
+ * over strips (each strip runs its own multigrid cycle). */
+LDC_API int ldc_solver_set_comm(ldc_solver *s, const ldc_comm_ops *ops);
 /* out3 = {Krylov iterations executed in lock step, sum over cavities of their own Krylov
  * iterations, Newton iterations (Jacobian builds) executed} since creation */
 LDC_API int ldc_solver_counters(ldc_solver *s, int64_t *out3);

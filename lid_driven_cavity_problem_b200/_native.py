@@ -75,6 +75,7 @@ SYMBOLS = {
     'ldc_solver_set_bc': (ctypes.c_int, [_vp, c_double_p]),
     'ldc_solver_set_state': (ctypes.c_int, [_vp, _vp, _vp]),
     'ldc_solver_get_state': (ctypes.c_int, [_vp, _vp, _vp]),
+    'ldc_solver_set_comm': (ctypes.c_int, [_vp, _vp]),
     'ldc_solver_num_levels': (ctypes.c_int, [_vp]),
     'ldc_solver_counters': (ctypes.c_int, [_vp, ctypes.POINTER(_i64)]),
     'ldc_solver_linear_solve': (ctypes.c_int, [_vp, _vp, _vp, c_int32_p, c_int32_p, c_double_p, _vp]),

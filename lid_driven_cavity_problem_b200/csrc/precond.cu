@@ -260,12 +260,32 @@ pressure_sum_partials_kernel(long N, const double *__restrict__ x, double *__res
 
 __global__ void __launch_bounds__(256)
 subtract_mean_pressure_kernel(long N, double *__restrict__ x, const double *__restrict__ sums,
-                              const int32_t *__restrict__ run)
+                              double n_cells, const int32_t *__restrict__ run)
 {
     const int b = blockIdx.y;
     if (run && !run[b]) return;
     const long c = (long)blockIdx.x * 256 + threadIdx.x;
-    if (c < N) x[(long)b * 3 * N + 3 * c] -= sums[b] / (double)N;
+    if (c < N) x[(long)b * 3 * N + 3 * c] -= sums[b] / n_cells;
+}
+
+// two-step form (a distributed solver all-reduces `sums` in between): sums[b] = sum of x_P,
+// then x_P -= sums[b] / n_cells_global
+int mg_pressure_sum(const MgLevel &l, const double *x, int batch, const int32_t *run,
+                    double *partials, double *sums, cudaStream_t s)
+{
+    const int nblk = (int)((l.N + 2047) / 2048);
+    pressure_sum_partials_kernel<<<dim3(nblk, batch), 256, 0, s>>>(l.N, x, partials, run);
+    LDC_CHECK_LAUNCH();
+    return vec_reduce_partials(partials, 1, nblk, batch, sums, s);
+}
+
+int mg_subtract_mean(const MgLevel &l, double *x, int batch, const int32_t *run, const double *sums,
+                     long n_cells_global, cudaStream_t s)
+{
+    subtract_mean_pressure_kernel<<<dim3((unsigned)((l.N + 255) / 256), batch), 256, 0, s>>>(
+        l.N, x, sums, (double)n_cells_global, run);
+    LDC_CHECK_LAUNCH();
+    return LDC_OK;
 }
 
 int mg_remove_mean_pressure(const MgLevel &l, double *x, int batch, const int32_t *run,
@@ -276,13 +296,8 @@ int mg_remove_mean_pressure(const MgLevel &l, double *x, int batch, const int32_
         LDC_CHECK_LAUNCH();
         return LDC_OK;
     }
-    const int nblk = (int)((l.N + 2047) / 2048);
-    pressure_sum_partials_kernel<<<dim3(nblk, batch), 256, 0, s>>>(l.N, x, partials, run);
-    LDC_CHECK_LAUNCH();
-    if (int rc = vec_reduce_partials(partials, 1, nblk, batch, sums, s)) return rc;
-    subtract_mean_pressure_kernel<<<dim3((unsigned)((l.N + 255) / 256), batch), 256, 0, s>>>(l.N, x, sums, run);
-    LDC_CHECK_LAUNCH();
-    return LDC_OK;
+    if (int rc = mg_pressure_sum(l, x, batch, run, partials, sums, s)) return rc;
+    return mg_subtract_mean(l, x, batch, run, sums, l.N, s);
 }
 
 static dim3 cell_grid(long N, int batch) { return dim3((unsigned)((N + 255) / 256), batch); }

@@ -117,9 +117,11 @@ __global__ void krylov_solve_y_kernel(KrylovSmall ks, int m, int kk, int batch, 
 
 // U_old, V_old <- the velocity slots of X (masked per instance)
 __global__ void __launch_bounds__(256)
-extract_old_kernel(int nx, int ny, const double *__restrict__ X, double *__restrict__ U_old,
+extract_old_kernel(int nx, int ny, int v_rows, const double *__restrict__ X, double *__restrict__ U_old,
                    double *__restrict__ V_old, const int32_t *__restrict__ run)
 {
+    // ny = rows held by this solver (grid rows, or the rows of a strip); v_rows = how many of them
+    // carry a real V (all but the top grid row)
     const int b = blockIdx.y;
     if (run && !run[b]) return;
     const long N = (long)nx * ny;
@@ -128,7 +130,7 @@ extract_old_kernel(int nx, int ny, const double *__restrict__ X, double *__restr
     const int j = (int)(c / nx), i = (int)(c - (long)j * nx);
     const double *x = X + 3 * ((long)b * N + c);
     if (i < nx - 1) U_old[(long)b * (nx - 1) * ny + i + (long)(nx - 1) * j] = x[1];
-    if (j < ny - 1) V_old[(long)b * nx * (ny - 1) + c] = x[2];
+    if (j < v_rows) V_old[(long)b * nx * v_rows + c] = x[2];
 }
 
 }  // namespace ldc
@@ -164,6 +166,11 @@ struct ldc_solver {
     // launches of one preconditioned iteration replay as a single graph launch.
     cudaStream_t stream;
     cudaEvent_t ev_in;
+    // row-strip decomposition
+    bool strip, ghost_lo, ghost_hi, has_comm;
+    ldc_comm_ops comm;
+    int v_rows;
+    double *X_alloc, *xpad_alloc, *xpad;
     bool use_graphs;
     std::vector<cudaGraphExec_t> iter_graph;
 
@@ -227,9 +234,12 @@ extern "C" void ldc_solver_default_options(ldc_solver_options *o)
     o->residual_variant = 0;
 }
 
-static ldc_grid level_grid(const ldc_solver *s, const MgLevel &l)
+static ldc_grid level_grid(const ldc_solver *s, const MgLevel &l, bool finest)
 {
     ldc_grid g = s->g;
+    // the finest level of a strip is the strip itself (true couplings to the halo rows); every
+    // coarser level treats the strip as a stand-alone cavity (block-Jacobi over strips)
+    if (finest) return g;
     g.nx = l.nx;
     g.ny = l.ny;
     g.row_begin = 0;
@@ -245,7 +255,7 @@ extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *op
 {
     LDC_REQUIRE(out != nullptr, "ldc_solver_create: out is NULL");
     *out = nullptr;
-    TRY(validate_grid(g, true));
+    TRY(validate_grid(g, false));
     ldc_solver_options o;
     if (opt) o = *opt; else ldc_solver_default_options(&o);
     LDC_REQUIRE(o.gmres_restart >= 1 && o.gmres_restart <= kMaxRestart, "gmres_restart must be in [1,%d]", kMaxRestart);
@@ -256,7 +266,14 @@ extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *op
     s->opt = o;
     s->batch = g->batch;
     s->m = o.gmres_restart;
-    s->N = (long)g->nx * g->ny;
+    s->strip = !(g->row_begin == 0 && g->row_count == g->ny);
+    s->ghost_lo = g->row_begin > 0;
+    s->ghost_hi = g->row_begin + g->row_count < g->ny;
+    s->has_comm = false;
+    memset(&s->comm, 0, sizeof(s->comm));
+    s->v_rows = (g->row_begin + g->row_count < g->ny ? g->row_count : g->ny - 1 - g->row_begin);
+    if (s->v_rows < 0) s->v_rows = 0;
+    s->N = (long)g->nx * g->row_count;   // cells held by this solver (a whole cavity or its row strip)
     s->n = 3 * s->N;
     s->nnz = ldc_mask_nnz(g->nx, g->ny, 3);
     s->total_linear_its = 0;
@@ -269,18 +286,23 @@ extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *op
     const long n = s->n;
     int rc = LDC_OK;
 #define A(expr) do { if (rc == LDC_OK) rc = (expr); } while (0)
-    A(s->dalloc(&s->X, (size_t)B * n));
+    // the state and the SpMV input of a strip carry one ghost row below and above
+    const long row = 3L * g->nx;
+    A(s->dalloc(&s->X_alloc, (size_t)B * n + 2 * row));
+    s->X = s->X_alloc ? s->X_alloc + row : nullptr;
+    A(s->dalloc(&s->xpad_alloc, (size_t)n + 2 * row));
+    s->xpad = s->xpad_alloc ? s->xpad_alloc + row : nullptr;
     A(s->dalloc(&s->X_prev, (size_t)B * n));
     A(s->dalloc(&s->F, (size_t)B * n));
     A(s->dalloc(&s->Y, (size_t)B * n));
-    A(s->dalloc(&s->U_old, (size_t)B * (g->nx - 1) * g->ny));
-    A(s->dalloc(&s->V_old, (size_t)B * g->nx * (g->ny - 1)));
+    A(s->dalloc(&s->U_old, (size_t)B * (g->nx - 1) * g->row_count));
+    A(s->dalloc(&s->V_old, (size_t)B * g->nx * g->row_count));
     A(s->dalloc(&s->dt_dev, B));
     A(s->dalloc(&s->bc_dev, B));
     // multigrid hierarchy
     int nlev = 1;
     if (o.pc_type == LDC_PC_MG_VANKA) {
-        int nx = g->nx, ny = g->ny;
+        int nx = g->nx, ny = g->row_count;
         const int min_size = o.mg_min_size > 2 ? o.mg_min_size : 3;
         while (nx % 2 == 0 && ny % 2 == 0 && nx / 2 >= min_size && ny / 2 >= min_size &&
                (o.mg_levels <= 0 || nlev < o.mg_levels)) {
@@ -291,7 +313,7 @@ extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *op
     for (int l = 0; l < nlev && rc == LDC_OK; ++l) {
         MgLevel &L = s->levels[l];
         L.nx = g->nx >> l;
-        L.ny = g->ny >> l;
+        L.ny = g->row_count >> l;
         L.dx = g->dx * (double)(1 << l);
         L.dy = g->dy * (double)(1 << l);
         L.N = (long)L.nx * L.ny;
@@ -348,7 +370,8 @@ extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *op
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMemcpy(s->dt_dev, s->dt_host.data(), sizeof(double) * B, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(s->bc_dev, s->bc_host.data(), sizeof(double) * B, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemset(s->X, 0, sizeof(double) * B * n);
+    if (e == cudaSuccess) e = cudaMemset(s->X_alloc, 0, sizeof(double) * ((size_t)B * n + 2 * row));
+    if (e == cudaSuccess) e = cudaMemset(s->xpad_alloc, 0, sizeof(double) * ((size_t)n + 2 * row));
     if (e != cudaSuccess) {
         ldc_solver_destroy(s);
         return cuda_fail(e, "solver init", __FILE__, __LINE__);
@@ -371,6 +394,17 @@ extern "C" void ldc_solver_destroy(ldc_solver *s)
 }
 
 extern "C" double *ldc_solver_state_dev(ldc_solver *s) { return s ? s->X : nullptr; }
+
+extern "C" int ldc_solver_set_comm(ldc_solver *s, const ldc_comm_ops *ops)
+{
+    LDC_REQUIRE(s && ops && ops->halo_exchange && ops->allreduce, "ldc_solver_set_comm: incomplete function table");
+    LDC_REQUIRE(s->batch == 1, "a distributed solver holds one cavity");
+    s->comm = *ops;
+    s->has_comm = true;
+    // NCCL calls are not replayed from CUDA graphs in this version
+    s->use_graphs = false;
+    return LDC_OK;
+}
 
 extern "C" int ldc_solver_num_levels(ldc_solver *s) { return s ? (int)s->levels.size() : 0; }
 
@@ -434,13 +468,46 @@ static bool any(const std::vector<int32_t> &m)
     return false;
 }
 
+// ---- row-strip helpers -----------------------------------------------------------------------
+static int comm_allreduce(ldc_solver *s, double *buf, long count, int op, cudaStream_t st)
+{
+    if (!s->has_comm || s->comm.nranks <= 1) return LDC_OK;
+    if (s->comm.allreduce(s->comm.ctx, buf, count, op, st) != 0) {
+        set_error("comm all-reduce failed");
+        return LDC_ERR_STATE;
+    }
+    return LDC_OK;
+}
+
+static int comm_halo(ldc_solver *s, double *first_owned_row, cudaStream_t st)
+{
+    if (!s->has_comm || s->comm.nranks <= 1) return LDC_OK;
+    if (s->comm.halo_exchange(s->comm.ctx, first_owned_row, 3L * s->g.nx, s->g.row_count, st) != 0) {
+        set_error("comm halo exchange failed");
+        return LDC_ERR_STATE;
+    }
+    return LDC_OK;
+}
+
+// y = J x or b - J x with the TRUE operator: a strip first refreshes the halo rows of x
+static int spmv_outer(ldc_solver *s, const double *x, const double *b, double *y, cudaStream_t st)
+{
+    const MgLevel &L0 = s->levels[0];
+    if (!s->strip)
+        return spmv_compact_launch(L0.nx, L0.ny, s->batch, L0.J, x, b, y, s->run_dev, st);
+    TRY(vec_copy(x, s->xpad, s->n, 1, nullptr, st));
+    TRY(comm_halo(s, s->xpad, st));
+    return spmv_compact_launch(L0.nx, L0.ny, 1, L0.J, s->xpad, b, y, s->run_dev, st, s->ghost_lo, s->ghost_hi);
+}
+
 // Jacobian at the current state on every level + diagonals
 static int build_hierarchy(ldc_solver *s, cudaStream_t st)
 {
+    TRY(comm_halo(s, s->X, st));   // the strip's Jacobian rows read the neighbours' boundary rows
     for (size_t l = 0; l < s->levels.size(); ++l) {
         MgLevel &L = s->levels[l];
         if (l > 0) TRY(mg_restrict_state(s->levels[l - 1], L, s->batch, st));
-        ldc_grid gl = level_grid(s, L);
+        ldc_grid gl = level_grid(s, L, l == 0);
         TRY(fd_jacobian_launch(&gl, L.X, s->U_old, s->V_old, nullptr, L.J, st));
         if (s->opt.pc_type != LDC_PC_NONE) TRY(mg_extract_diag(L, s->batch, st));
     }
@@ -482,7 +549,10 @@ static int apply_pc(ldc_solver *s, const double *v, double *z, const int32_t *ru
     // The Jacobian is singular by the constant-pressure mode (with finite-difference
     // noise: nearly singular).  Searching only among zero-mean pressure corrections keeps the
     // Krylov solution out of that mode (what KSPSetNullSpace does in PETSc).
-    return mg_remove_mean_pressure(s->levels[0], z, s->batch, run, s->partials, s->ks.hcol2, st);
+    if (!s->strip) return mg_remove_mean_pressure(s->levels[0], z, s->batch, run, s->partials, s->ks.hcol2, st);
+    TRY(mg_pressure_sum(s->levels[0], z, 1, run, s->partials, s->ks.hcol2, st));
+    TRY(comm_allreduce(s, s->ks.hcol2, 1, 0, st));
+    return mg_subtract_mean(s->levels[0], z, 1, run, s->ks.hcol2, (long)s->g.nx * s->g.ny, st);
 }
 
 // squared norm of x per instance -> dst_dev[b]
@@ -491,7 +561,7 @@ static int norm2_to(ldc_solver *s, const double *x, double *dst_dev, const int32
     const int nblk = dot_blocks(s->n);
     TRY(vec_norm2_partials(x, s->n, s->batch, run, s->partials, st));
     TRY(vec_reduce_partials(s->partials, 1, nblk, s->batch, dst_dev, st));
-    return LDC_OK;
+    return comm_allreduce(s, dst_dev, s->batch, 0, st);
 }
 
 // every launch of Krylov iteration k: z_k = M v_k, w = J z_k, Gram-Schmidt against v_0..v_k,
@@ -507,20 +577,23 @@ static int krylov_iteration_body(ldc_solver *s, int k, cudaStream_t st)
     const int tb = 64, gb = (B + tb - 1) / tb;
     double *vk = s->V + (long)k * vs, *zk = s->Z + (long)k * vs;
     TRY(apply_pc(s, vk, zk, s->run_dev, st));
-    TRY(spmv_compact_launch(L0.nx, L0.ny, B, L0.J, zk, nullptr, s->w, s->run_dev, st));
+    TRY(spmv_outer(s, zk, nullptr, s->w, st));
     TRY(vec_multi_dot(s->V, vs, k + 1, s->w, n, B, s->run_dev, s->partials, st));
     TRY(vec_reduce_partials(s->partials, k + 1, nblk, B, s->ks.hcol, st));
+    TRY(comm_allreduce(s, s->ks.hcol, (long)B * (k + 1), 0, st));
     TRY(vec_gs_update(s->V, vs, k + 1, s->ks.hcol, k + 1, s->w, n, B, s->run_dev, s->partials, st));
     if (o.gmres_refine) {
         // second classical Gram-Schmidt pass (CGS2): keeps the basis orthogonal to working
         // precision so the residual estimate stays equal to the true residual
         TRY(vec_multi_dot(s->V, vs, k + 1, s->w, n, B, s->run_dev, s->partials, st));
         TRY(vec_reduce_partials(s->partials, k + 1, nblk, B, s->ks.hcol2, st));
+        TRY(comm_allreduce(s, s->ks.hcol2, (long)B * (k + 1), 0, st));
         TRY(vec_gs_update(s->V, vs, k + 1, s->ks.hcol2, k + 1, s->w, n, B, s->run_dev, s->partials, st));
         add_columns_kernel<<<(B * (k + 1) + 127) / 128, 128, 0, st>>>(s->ks.hcol, s->ks.hcol2, B * (k + 1));
         LDC_CHECK_LAUNCH();
     }
     TRY(vec_reduce_partials(s->partials, 1, nblk, B, s->ks.nrm2, st));
+    TRY(comm_allreduce(s, s->ks.nrm2, B, 0, st));
     krylov_givens_kernel<<<gb, tb, 0, st>>>(s->ks, m, k, B, s->run_dev);
     LDC_CHECK_LAUNCH();
     TRY(vec_scale_dev(s->w, s->ks.hnext, 1, true, s->V + (long)(k + 1) * vs, n, B, s->run_dev, st));
@@ -618,7 +691,7 @@ static int fgmres(ldc_solver *s, const double *rhs, double *y, std::vector<int32
         krylov_solve_y_kernel<<<gb, tb, 0, st>>>(s->ks, m, k, B, s->run_dev);
         LDC_CHECK_LAUNCH();
         TRY(vec_multi_axpy(s->Z, vs, k, s->ks.yv, m, y, n, B, s->run_dev, st));
-        TRY(spmv_compact_launch(L0.nx, L0.ny, B, L0.J, y, rhs, s->rres, s->run_dev, st));
+        TRY(spmv_outer(s, y, rhs, s->rres, st));
         TRY(norm2_to(s, s->rres, s->ks.nrm2, s->run_dev, st));
         sqrt_kernel<<<gb, tb, 0, st>>>(s->ks.nrm2, s->ks.beta, B, s->run_dev);
         LDC_CHECK_LAUNCH();
@@ -628,8 +701,10 @@ static int fgmres(ldc_solver *s, const double *rhs, double *y, std::vector<int32
 
 static int residual_and_norm(ldc_solver *s, double *norm2_dst, cudaStream_t st)
 {
-    return ldc_residual(&s->g, s->X, s->U_old, s->V_old, s->F, norm2_dst, s->res_work,
-                        s->opt.residual_variant, st);
+    TRY(comm_halo(s, s->X, st));
+    TRY(ldc_residual(&s->g, s->X, s->U_old, s->V_old, s->F, norm2_dst, s->res_work,
+                     s->opt.residual_variant, st));
+    return norm2_dst ? comm_allreduce(s, norm2_dst, s->batch, 0, st) : LDC_OK;
 }
 
 extern "C" int ldc_solver_linear_solve(ldc_solver *s, const double *rhs_dev, double *y_dev,
@@ -644,7 +719,7 @@ extern "C" int ldc_solver_linear_solve(ldc_solver *s, const double *rhs_dev, dou
     std::vector<int32_t> all(B, 1);
     TRY(upload_mask(s, all, s->run_dev, st));
     extract_old_kernel<<<dim3((unsigned)((s->N + 255) / 256), B), 256, 0, st>>>(
-        s->g.nx, s->g.ny, s->X, s->U_old, s->V_old, s->run_dev);
+        s->g.nx, s->g.row_count, s->v_rows, s->X, s->U_old, s->V_old, s->run_dev);
     LDC_CHECK_LAUNCH();
     TRY(build_hierarchy(s, st));
     TRY(norm2_to(s, rhs_dev, s->scal_dev, nullptr, st));
@@ -684,7 +759,7 @@ extern "C" int ldc_solver_step(ldc_solver *s, const int32_t *active_host, ldc_ne
     TRY(upload_mask(s, act, s->run_dev, st));
     TRY(vec_copy(s->X, s->X_prev, n, B, s->run_dev, st));
     extract_old_kernel<<<dim3((unsigned)((s->N + 255) / 256), B), 256, 0, st>>>(
-        s->g.nx, s->g.ny, s->X, s->U_old, s->V_old, s->run_dev);
+        s->g.nx, s->g.row_count, s->v_rows, s->X, s->U_old, s->V_old, s->run_dev);
     LDC_CHECK_LAUNCH();
 
     TRY(residual_and_norm(s, s->scal_dev, st));
@@ -757,7 +832,8 @@ extern "C" int ldc_solver_step(ldc_solver *s, const int32_t *active_host, ldc_ne
         TRY(vec_copy(s->X_prev, s->X, n, B, s->fin_dev, st));
     }
     if (du_inf_host) {
-        TRY(vec_du_inf(s->X, s->U_old, s->g.nx, s->g.ny, B, s->ks.nrm2, st));
+        TRY(vec_du_inf(s->X, s->U_old, s->g.nx, s->g.row_count, B, s->ks.nrm2, st));
+        TRY(comm_allreduce(s, s->ks.nrm2, B, 1, st));
         LDC_CUDA(cudaMemcpyAsync(s->du_host, s->ks.nrm2, sizeof(double) * B, cudaMemcpyDeviceToHost, st));
     }
     LDC_CUDA(cudaStreamSynchronize(st));

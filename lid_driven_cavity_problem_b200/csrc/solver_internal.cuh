@@ -83,6 +83,10 @@ int mg_restrict_residual(const MgLevel &f, const double *r_f, const MgLevel &c, 
 // x_P -= mean(x_P) per instance; partials/sums are scratch (>= batch*ceil(N/2048) and batch doubles)
 int mg_remove_mean_pressure(const MgLevel &l, double *x, int batch, const int32_t *run,
                             double *partials, double *sums, cudaStream_t s);
+int mg_pressure_sum(const MgLevel &l, const double *x, int batch, const int32_t *run,
+                    double *partials, double *sums, cudaStream_t s);
+int mg_subtract_mean(const MgLevel &l, double *x, int batch, const int32_t *run, const double *sums,
+                     long n_cells_global, cudaStream_t s);
 int mg_prolong_add(const MgLevel &c, const double *x_c, const MgLevel &f, double *x_f, int batch,
                    const int32_t *run, cudaStream_t s);
 
