@@ -23,7 +23,7 @@ namespace ldc {
 // coarse face; coarse dummy slots = 0.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-restrict_state_kernel(int nxf, int nyf, const double *__restrict__ Xf, double *__restrict__ Xc)
+restrict_state_kernel(int nxf, int nyf, int v_rows_c, const double *__restrict__ Xf, double *__restrict__ Xc)
 {
     const int nxc = nxf / 2, nyc = nyf / 2;
     const long Nc = (long)nxc * nyc;
@@ -37,7 +37,7 @@ restrict_state_kernel(int nxf, int nyf, const double *__restrict__ Xf, double *_
     const int i0 = 2 * I, j0 = 2 * J;
     Xc[3 * c] = 0.25 * (f(i0, j0, 0) + f(i0 + 1, j0, 0) + f(i0, j0 + 1, 0) + f(i0 + 1, j0 + 1, 0));
     Xc[3 * c + 1] = (I < nxc - 1) ? 0.5 * (f(i0 + 1, j0, 1) + f(i0 + 1, j0 + 1, 1)) : 0.0;
-    Xc[3 * c + 2] = (J < nyc - 1) ? 0.5 * (f(i0, j0 + 1, 2) + f(i0 + 1, j0 + 1, 2)) : 0.0;
+    Xc[3 * c + 2] = (J < v_rows_c) ? 0.5 * (f(i0, j0 + 1, 2) + f(i0 + 1, j0 + 1, 2)) : 0.0;
 }
 
 // diagonal of J from the compact layout: U rows -> k=9 (U_P), V rows -> k=20 (V_P); continuity
@@ -64,10 +64,12 @@ extract_diag_kernel(long N, const double *__restrict__ Jc, double *__restrict__ 
 //  => dp = (sum_k d_k r_k / a_k - r_c) / (sum_k d_k g_k / a_k),   du_k = (r_k - g_k dp) / a_k
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-vanka_dp_kernel(int nx, int ny, double dx, double dy, const double *__restrict__ r,
+vanka_dp_kernel(int nx, int ny, int v_rows, double dx, double dy, const double *__restrict__ r,
                 const double *__restrict__ diag, double *__restrict__ dp,
                 const int32_t *__restrict__ run)
 {
+    // ny = held rows, v_rows = held rows with a real V.  Across a strip boundary the relaxation is
+    // decoupled: the south face of the first held row belongs to the strip below and is left out.
     const int b = blockIdx.y;
     if (run && !run[b]) return;
     const long N = (long)nx * ny;
@@ -88,7 +90,7 @@ vanka_dp_kernel(int nx, int ny, double dx, double dy, const double *__restrict__
         num -= dy * r[3 * (c - 1) + 1] * ia;
         den -= dy * dy * ia;
     }
-    if (j < ny - 1) {  // north face: V row of cell c, d=+dx, g=-dx
+    if (j < v_rows) {  // north face: V row of cell c, d=+dx, g=-dx
         const double ia = 1.0 / diag[3 * c + 2];
         num += dx * r[3 * c + 2] * ia;
         den -= dx * dx * ia;
@@ -104,7 +106,7 @@ vanka_dp_kernel(int nx, int ny, double dx, double dy, const double *__restrict__
 // x (+)= omega * correction ; ASSIGN: x is taken as zero before the sweep
 template <bool ASSIGN>
 __global__ void __launch_bounds__(256)
-vanka_update_kernel(int nx, int ny, double dx, double dy, double om_u, double om_p,
+vanka_update_kernel(int nx, int ny, int v_rows, double dx, double dy, double om_u, double om_p,
                     const double *__restrict__ r, const double *__restrict__ diag,
                     const double *__restrict__ dp, double *__restrict__ x,
                     const int32_t *__restrict__ run)
@@ -128,9 +130,11 @@ vanka_update_kernel(int nx, int ny, double dx, double dy, double om_u, double om
     } else {
         e1 = r[3 * c + 1] / diag[3 * c + 1];  // dummy row (identity)
     }
-    if (j < ny - 1) {
+    if (j < v_rows) {
         const double rv = r[3 * c + 2];
-        e2 = 0.5 * om_u * ((rv + dx * p_c) + (rv - dx * dp[c + nx])) / diag[3 * c + 2];
+        // the cell above is in the next strip for the last held row of a strip: decoupled (dp = 0)
+        const double p_above = (j + 1 < ny) ? dp[c + nx] : 0.0;
+        e2 = 0.5 * om_u * ((rv + dx * p_c) + (rv - dx * p_above)) / diag[3 * c + 2];
     } else {
         e2 = r[3 * c + 2] / diag[3 * c + 2];
     }
@@ -151,9 +155,11 @@ vanka_update_kernel(int nx, int ny, double dx, double dy, double om_u, double om
 //   both fine rows;  V rows: transposed.  Coarse dummy rows get 0.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-restrict_residual_kernel(int nxf, int nyf, const double *__restrict__ rf, double *__restrict__ bc,
-                         const int32_t *__restrict__ run)
+restrict_residual_kernel(int nxf, int nyf, int v_rows_c, const double *__restrict__ rf,
+                         double *__restrict__ bc, const int32_t *__restrict__ run)
 {
+    // a real coarse V row (J < v_rows_c) reads fine row 2J+2, which for the last coarse row of a
+    // strip is the halo row above the fine strip (rf carries it)
     const int b = blockIdx.y;
     if (run && !run[b]) return;
     const int nxc = nxf / 2, nyc = nyf / 2;
@@ -171,7 +177,7 @@ restrict_residual_kernel(int nxf, int nyf, const double *__restrict__ rf, double
         u = 0.5 * (f(i0, j0, 1) + f(i0, j0 + 1, 1)) + (f(i0 + 1, j0, 1) + f(i0 + 1, j0 + 1, 1)) +
             0.5 * (f(i0 + 2, j0, 1) + f(i0 + 2, j0 + 1, 1));
     }
-    if (J < nyc - 1) {
+    if (J < v_rows_c) {
         v = 0.5 * (f(i0, j0, 2) + f(i0 + 1, j0, 2)) + (f(i0, j0 + 1, 2) + f(i0 + 1, j0 + 1, 2)) +
             0.5 * (f(i0, j0 + 2, 2) + f(i0 + 1, j0 + 2, 2));
     }
@@ -181,9 +187,11 @@ restrict_residual_kernel(int nxf, int nyf, const double *__restrict__ rf, double
 
 // prolongation = transpose of the restriction above, added to the fine correction
 __global__ void __launch_bounds__(256)
-prolong_add_kernel(int nxf, int nyf, const double *__restrict__ xc, double *__restrict__ xf,
+prolong_add_kernel(int nxf, int nyf, int v_rows_f, int v_rows_c, int ghost_lo_c,
+                   const double *__restrict__ xc, double *__restrict__ xf,
                    const int32_t *__restrict__ run)
 {
+    // xc carries the halo row below a strip (coarse row -1) when ghost_lo_c is set
     const int b = blockIdx.y;
     if (run && !run[b]) return;
     const int nxc = nxf / 2, nyc = nyf / 2;
@@ -202,10 +210,10 @@ prolong_add_kernel(int nxf, int nyf, const double *__restrict__ xc, double *__re
         else u = 0.5 * ((I >= 1 ? g(I - 1, J, 1) : 0.0) + (I < nxc - 1 ? g(I, J, 1) : 0.0));
         xf[3 * c + 1] += u;
     }
-    if (j < nyf - 1) {
+    if (j < v_rows_f) {
         double v;
         if (j & 1) v = g(I, J, 2);
-        else v = 0.5 * ((J >= 1 ? g(I, J - 1, 2) : 0.0) + (J < nyc - 1 ? g(I, J, 2) : 0.0));
+        else v = 0.5 * (((J >= 1 || ghost_lo_c) ? g(I, J - 1, 2) : 0.0) + (J < v_rows_c ? g(I, J, 2) : 0.0));
         xf[3 * c + 2] += v;
     }
 }
@@ -304,7 +312,7 @@ static dim3 cell_grid(long N, int batch) { return dim3((unsigned)((N + 255) / 25
 
 int mg_restrict_state(const MgLevel &f, const MgLevel &c, int batch, cudaStream_t s)
 {
-    restrict_state_kernel<<<cell_grid(c.N, batch), 256, 0, s>>>(f.nx, f.ny, f.X, c.X);
+    restrict_state_kernel<<<cell_grid(c.N, batch), 256, 0, s>>>(f.nx, f.ny, c.v_rows, f.X, c.X);
     LDC_CHECK_LAUNCH();
     return LDC_OK;
 }
@@ -312,6 +320,19 @@ int mg_restrict_state(const MgLevel &f, const MgLevel &c, int batch, cudaStream_
 int mg_extract_diag(const MgLevel &l, int batch, cudaStream_t s)
 {
     extract_diag_kernel<<<cell_grid(l.N, batch), 256, 0, s>>>(l.N, l.J, l.diag);
+    LDC_CHECK_LAUNCH();
+    return LDC_OK;
+}
+
+int mg_vanka_relax(const MgLevel &l, const double *r, double *x, bool assign, double om_u, double om_p,
+                   int batch, const int32_t *run, cudaStream_t s)
+{
+    vanka_dp_kernel<<<cell_grid(l.N, batch), 256, 0, s>>>(l.nx, l.ny, l.v_rows, l.dx, l.dy, r, l.diag, l.dp, run);
+    LDC_CHECK_LAUNCH();
+    if (assign)
+        vanka_update_kernel<true><<<cell_grid(l.N, batch), 256, 0, s>>>(l.nx, l.ny, l.v_rows, l.dx, l.dy, om_u, om_p, r, l.diag, l.dp, x, run);
+    else
+        vanka_update_kernel<false><<<cell_grid(l.N, batch), 256, 0, s>>>(l.nx, l.ny, l.v_rows, l.dx, l.dy, om_u, om_p, r, l.diag, l.dp, x, run);
     LDC_CHECK_LAUNCH();
     return LDC_OK;
 }
@@ -324,20 +345,13 @@ int mg_vanka_sweep(const MgLevel &l, const double *b, double *x, bool zero_guess
         if (int rc = spmv_compact_launch(l.nx, l.ny, batch, l.J, x, b, l.r, run, s)) return rc;
         r = l.r;
     }
-    vanka_dp_kernel<<<cell_grid(l.N, batch), 256, 0, s>>>(l.nx, l.ny, l.dx, l.dy, r, l.diag, l.dp, run);
-    LDC_CHECK_LAUNCH();
-    if (zero_guess)
-        vanka_update_kernel<true><<<cell_grid(l.N, batch), 256, 0, s>>>(l.nx, l.ny, l.dx, l.dy, om_u, om_p, r, l.diag, l.dp, x, run);
-    else
-        vanka_update_kernel<false><<<cell_grid(l.N, batch), 256, 0, s>>>(l.nx, l.ny, l.dx, l.dy, om_u, om_p, r, l.diag, l.dp, x, run);
-    LDC_CHECK_LAUNCH();
-    return LDC_OK;
+    return mg_vanka_relax(l, r, x, zero_guess, om_u, om_p, batch, run, s);
 }
 
 int mg_restrict_residual(const MgLevel &f, const double *r_f, const MgLevel &c, double *b_c,
                          int batch, const int32_t *run, cudaStream_t s)
 {
-    restrict_residual_kernel<<<cell_grid(c.N, batch), 256, 0, s>>>(f.nx, f.ny, r_f, b_c, run);
+    restrict_residual_kernel<<<cell_grid(c.N, batch), 256, 0, s>>>(f.nx, f.ny, c.v_rows, r_f, b_c, run);
     LDC_CHECK_LAUNCH();
     return LDC_OK;
 }
@@ -345,7 +359,7 @@ int mg_restrict_residual(const MgLevel &f, const double *r_f, const MgLevel &c, 
 int mg_prolong_add(const MgLevel &c, const double *x_c, const MgLevel &f, double *x_f, int batch,
                    const int32_t *run, cudaStream_t s)
 {
-    prolong_add_kernel<<<cell_grid(f.N, batch), 256, 0, s>>>(f.nx, f.ny, x_c, x_f, run);
+    prolong_add_kernel<<<cell_grid(f.N, batch), 256, 0, s>>>(f.nx, f.ny, f.v_rows, c.v_rows, c.ghost_lo ? 1 : 0, x_c, x_f, run);
     LDC_CHECK_LAUNCH();
     return LDC_OK;
 }

@@ -171,6 +171,7 @@ struct ldc_solver {
     ldc_comm_ops comm;
     int v_rows;
     double *X_alloc, *xpad_alloc, *xpad;
+    long zs;   // distance between preconditioned basis vectors Z_k (each padded by a halo row on both sides)
     bool use_graphs;
     std::vector<cudaGraphExec_t> iter_graph;
 
@@ -234,15 +235,12 @@ extern "C" void ldc_solver_default_options(ldc_solver_options *o)
     o->residual_variant = 0;
 }
 
-static ldc_grid level_grid(const ldc_solver *s, const MgLevel &l, bool finest)
+static ldc_grid level_grid(const ldc_solver *s, const MgLevel &l)
 {
     ldc_grid g = s->g;
-    // the finest level of a strip is the strip itself (true couplings to the halo rows); every
-    // coarser level treats the strip as a stand-alone cavity (block-Jacobi over strips)
-    if (finest) return g;
     g.nx = l.nx;
-    g.ny = l.ny;
-    g.row_begin = 0;
+    g.ny = l.ny_global;
+    g.row_begin = l.row_begin;
     g.row_count = l.ny;
     g.dx = l.dx;
     g.dy = l.dy;
@@ -299,14 +297,16 @@ extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *op
     A(s->dalloc(&s->V_old, (size_t)B * g->nx * g->row_count));
     A(s->dalloc(&s->dt_dev, B));
     A(s->dalloc(&s->bc_dev, B));
-    // multigrid hierarchy
+    // multigrid hierarchy.  A strip coarsens its own rows; strip boundaries stay aligned because the
+    // partition is a multiple of 2^levels rows (strip_partition).
     int nlev = 1;
     if (o.pc_type == LDC_PC_MG_VANKA) {
-        int nx = g->nx, ny = g->row_count;
+        int nx = g->nx, ny = g->row_count, rb = g->row_begin, nyg = g->ny;
         const int min_size = o.mg_min_size > 2 ? o.mg_min_size : 3;
-        while (nx % 2 == 0 && ny % 2 == 0 && nx / 2 >= min_size && ny / 2 >= min_size &&
-               (o.mg_levels <= 0 || nlev < o.mg_levels)) {
-            nx /= 2; ny /= 2; ++nlev;
+        const int min_rows = s->strip ? 2 : min_size;
+        while (nx % 2 == 0 && ny % 2 == 0 && rb % 2 == 0 && nyg % 2 == 0 && nx / 2 >= min_size &&
+               ny / 2 >= min_rows && (o.mg_levels <= 0 || nlev < o.mg_levels)) {
+            nx /= 2; ny /= 2; rb /= 2; nyg /= 2; ++nlev;
         }
     }
     s->levels.resize(nlev);
@@ -314,26 +314,48 @@ extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *op
         MgLevel &L = s->levels[l];
         L.nx = g->nx >> l;
         L.ny = g->row_count >> l;
+        L.row_begin = g->row_begin >> l;
+        L.ny_global = g->ny >> l;
+        L.ghost_lo = s->ghost_lo;
+        L.ghost_hi = s->ghost_hi;
+        L.v_rows = (L.row_begin + L.ny < L.ny_global) ? L.ny : L.ny_global - 1 - L.row_begin;
+        if (L.v_rows < 0) L.v_rows = 0;
         L.dx = g->dx * (double)(1 << l);
         L.dy = g->dy * (double)(1 << l);
         L.N = (long)L.nx * L.ny;
         L.n = 3 * L.N;
-        L.nnz = ldc_mask_nnz(L.nx, L.ny, 3);
+        L.nnz = 0;
         L.X = nullptr; L.x = L.b = nullptr;
+        const long lrow = 3L * L.nx;   // every level vector has a spare (halo) row on both sides
+        auto padded = [&](double **p) {
+            double *q = nullptr;
+            int r2 = s->dalloc(&q, (size_t)B * L.n + 2 * lrow);
+            if (r2 == LDC_OK) {
+                cudaMemset(q, 0, sizeof(double) * ((size_t)B * L.n + 2 * lrow));
+                *p = q + lrow;
+            }
+            return r2;
+        };
         if (l == 0) L.X = s->X;
         else {
-            A(s->dalloc(&L.X, (size_t)B * L.n));
-            A(s->dalloc(&L.x, (size_t)B * L.n));
-            A(s->dalloc(&L.b, (size_t)B * L.n));
+            A(padded(&L.X));
+            A(padded(&L.x));
+            A(padded(&L.b));
         }
         A(s->dalloc(&L.J, (size_t)B * 26 * L.N));
         A(s->dalloc(&L.diag, (size_t)B * L.n));
-        A(s->dalloc(&L.r, (size_t)B * L.n));
+        A(padded(&L.r));
         A(s->dalloc(&L.dp, (size_t)B * L.N));
     }
     // Krylov workspace
     A(s->dalloc(&s->V, (size_t)(m + 1) * B * n));
-    A(s->dalloc(&s->Z, (size_t)m * B * n));
+    s->zs = (long)B * n + 2 * row;
+    {
+        double *zq = nullptr;
+        A(s->dalloc(&zq, (size_t)m * s->zs));
+        if (zq) cudaMemset(zq, 0, sizeof(double) * (size_t)m * s->zs);
+        s->Z = zq ? zq + row : nullptr;
+    }
     A(s->dalloc(&s->w, (size_t)B * n));
     A(s->dalloc(&s->rres, (size_t)B * n));
     const int nblk = dot_blocks(n);
@@ -489,59 +511,101 @@ static int comm_halo(ldc_solver *s, double *first_owned_row, cudaStream_t st)
     return LDC_OK;
 }
 
-// y = J x or b - J x with the TRUE operator: a strip first refreshes the halo rows of x
+static int level_halo(ldc_solver *s, const MgLevel &L, double *first_owned_row, cudaStream_t st)
+{
+    if (!s->has_comm || s->comm.nranks <= 1) return LDC_OK;
+    if (s->comm.halo_exchange(s->comm.ctx, first_owned_row, 3L * L.nx, L.ny, st) != 0) {
+        set_error("comm halo exchange failed");
+        return LDC_ERR_STATE;
+    }
+    return LDC_OK;
+}
+
+// y = J_l x or b - J_l x with the true rows of level l; x must be a padded vector (its halo rows
+// are refreshed here for a strip)
+static int level_spmv(ldc_solver *s, const MgLevel &L, double *x_padded, const double *b, double *y,
+                      const int32_t *run, cudaStream_t st)
+{
+    TRY(level_halo(s, L, x_padded, st));
+    return spmv_compact_launch(L.nx, L.ny, s->batch, L.J, x_padded, b, y, run, st, L.ghost_lo, L.ghost_hi);
+}
+
+// same for an unpadded x (copied into the padded scratch first; strips only)
 static int spmv_outer(ldc_solver *s, const double *x, const double *b, double *y, cudaStream_t st)
 {
     const MgLevel &L0 = s->levels[0];
     if (!s->strip)
         return spmv_compact_launch(L0.nx, L0.ny, s->batch, L0.J, x, b, y, s->run_dev, st);
     TRY(vec_copy(x, s->xpad, s->n, 1, nullptr, st));
-    TRY(comm_halo(s, s->xpad, st));
-    return spmv_compact_launch(L0.nx, L0.ny, 1, L0.J, s->xpad, b, y, s->run_dev, st, s->ghost_lo, s->ghost_hi);
+    return level_spmv(s, L0, s->xpad, b, y, s->run_dev, st);
 }
 
 // Jacobian at the current state on every level + diagonals
 static int build_hierarchy(ldc_solver *s, cudaStream_t st)
 {
-    TRY(comm_halo(s, s->X, st));   // the strip's Jacobian rows read the neighbours' boundary rows
     for (size_t l = 0; l < s->levels.size(); ++l) {
         MgLevel &L = s->levels[l];
         if (l > 0) TRY(mg_restrict_state(s->levels[l - 1], L, s->batch, st));
-        ldc_grid gl = level_grid(s, L, l == 0);
+        TRY(level_halo(s, L, L.X, st));   // a strip's Jacobian rows read the neighbours' boundary rows
+        ldc_grid gl = level_grid(s, L);
         TRY(fd_jacobian_launch(&gl, L.X, s->U_old, s->V_old, nullptr, L.J, st));
         if (s->opt.pc_type != LDC_PC_NONE) TRY(mg_extract_diag(L, s->batch, st));
     }
     return LDC_OK;
 }
 
+// one relaxation sweep x += omega B^-1 (b - J x); the residual uses the true operator (halo of x),
+// the cell-block solves are local to the strip
+static int sweep(ldc_solver *s, const MgLevel &L, const double *b, double *x, bool zero_guess,
+                 const int32_t *run, cudaStream_t st)
+{
+    const double *r = b;
+    if (!zero_guess) {
+        TRY(level_spmv(s, L, x, b, L.r, run, st));
+        r = L.r;
+    }
+    return mg_vanka_relax(L, r, x, zero_guess, s->opt.pc_omega_u, s->opt.pc_omega_p, s->batch, run, st);
+}
+
+// x_P -= mean(x_P) over the WHOLE level (all strips)
+static int remove_mean(ldc_solver *s, const MgLevel &L, double *x, const int32_t *run, cudaStream_t st)
+{
+    if (!s->strip) return mg_remove_mean_pressure(L, x, s->batch, run, s->partials, s->ks.hcol2, st);
+    TRY(mg_pressure_sum(L, x, 1, run, s->partials, s->ks.hcol2, st));
+    TRY(comm_allreduce(s, s->ks.hcol2, 1, 0, st));
+    return mg_subtract_mean(L, x, 1, run, s->ks.hcol2, (long)L.nx * L.ny_global, st);
+}
+
+// x must be a padded vector of level l
 static int vcycle(ldc_solver *s, size_t l, const double *b, double *x, const int32_t *run, cudaStream_t st)
 {
     const MgLevel &L = s->levels[l];
-    const double ou = s->opt.pc_omega_u, op = s->opt.pc_omega_p;
-    const int B = s->batch;
     if (l + 1 == s->levels.size()) {
         // the coarsest grid is relaxed until it is (roughly) solved: a few sweeps on a 4x4 grid,
         // ~2 per cell row when the grid could not be coarsened further (e.g. 100 -> 50 -> 25)
         int sweeps = s->opt.pc_sweeps;
         if (s->levels.size() > 1) {
             sweeps = s->opt.mg_coarse_sweeps;
-            const int side = L.nx > L.ny ? L.nx : L.ny;
+            const int side = L.nx > L.ny_global ? L.nx : L.ny_global;
             if (sweeps < 2 * side) sweeps = 2 * side;
         }
-        for (int k = 0; k < sweeps; ++k) TRY(mg_vanka_sweep(L, b, x, k == 0, ou, op, B, run, st));
-        if (s->levels.size() > 1) TRY(mg_remove_mean_pressure(L, x, B, run, nullptr, nullptr, st));
+        for (int k = 0; k < sweeps; ++k) TRY(sweep(s, L, b, x, k == 0, run, st));
+        if (s->levels.size() > 1) TRY(remove_mean(s, L, x, run, st));
         return LDC_OK;
     }
-    for (int k = 0; k < s->opt.pc_sweeps; ++k) TRY(mg_vanka_sweep(L, b, x, k == 0, ou, op, B, run, st));
-    TRY(spmv_compact_launch(L.nx, L.ny, B, L.J, x, b, L.r, run, st));
+    for (int k = 0; k < s->opt.pc_sweeps; ++k) TRY(sweep(s, L, b, x, k == 0, run, st));
+    TRY(level_spmv(s, L, x, b, L.r, run, st));
     const MgLevel &C = s->levels[l + 1];
-    TRY(mg_restrict_residual(L, L.r, C, C.b, B, run, st));
+    TRY(level_halo(s, L, L.r, st));   // the last coarse V row of a strip reads the fine row above it
+    TRY(mg_restrict_residual(L, L.r, C, C.b, s->batch, run, st));
     TRY(vcycle(s, l + 1, C.b, C.x, run, st));
-    TRY(mg_prolong_add(C, C.x, L, x, B, run, st));
-    for (int k = 0; k < s->opt.pc_sweeps; ++k) TRY(mg_vanka_sweep(L, b, x, false, ou, op, B, run, st));
+    TRY(level_halo(s, C, C.x, st));   // the first fine V row of a strip interpolates from below
+    TRY(mg_prolong_add(C, C.x, L, x, s->batch, run, st));
+    for (int k = 0; k < s->opt.pc_sweeps; ++k) TRY(sweep(s, L, b, x, false, run, st));
     return LDC_OK;
 }
 
+// z = M v ; z is a padded basis vector Z_k
 static int apply_pc(ldc_solver *s, const double *v, double *z, const int32_t *run, cudaStream_t st)
 {
     if (s->opt.pc_type == LDC_PC_NONE) return vec_copy(v, z, s->n, s->batch, run, st);
@@ -549,10 +613,7 @@ static int apply_pc(ldc_solver *s, const double *v, double *z, const int32_t *ru
     // The Jacobian is singular by the constant-pressure mode (with finite-difference
     // noise: nearly singular).  Searching only among zero-mean pressure corrections keeps the
     // Krylov solution out of that mode (what KSPSetNullSpace does in PETSc).
-    if (!s->strip) return mg_remove_mean_pressure(s->levels[0], z, s->batch, run, s->partials, s->ks.hcol2, st);
-    TRY(mg_pressure_sum(s->levels[0], z, 1, run, s->partials, s->ks.hcol2, st));
-    TRY(comm_allreduce(s, s->ks.hcol2, 1, 0, st));
-    return mg_subtract_mean(s->levels[0], z, 1, run, s->ks.hcol2, (long)s->g.nx * s->g.ny, st);
+    return remove_mean(s, s->levels[0], z, run, st);
 }
 
 // squared norm of x per instance -> dst_dev[b]
@@ -575,9 +636,9 @@ static int krylov_iteration_body(ldc_solver *s, int k, cudaStream_t st)
     const MgLevel &L0 = s->levels[0];
     const ldc_solver_options &o = s->opt;
     const int tb = 64, gb = (B + tb - 1) / tb;
-    double *vk = s->V + (long)k * vs, *zk = s->Z + (long)k * vs;
+    double *vk = s->V + (long)k * vs, *zk = s->Z + (long)k * s->zs;
     TRY(apply_pc(s, vk, zk, s->run_dev, st));
-    TRY(spmv_outer(s, zk, nullptr, s->w, st));
+    TRY(level_spmv(s, L0, zk, nullptr, s->w, s->run_dev, st));
     TRY(vec_multi_dot(s->V, vs, k + 1, s->w, n, B, s->run_dev, s->partials, st));
     TRY(vec_reduce_partials(s->partials, k + 1, nblk, B, s->ks.hcol, st));
     TRY(comm_allreduce(s, s->ks.hcol, (long)B * (k + 1), 0, st));
@@ -681,7 +742,7 @@ static int fgmres(ldc_solver *s, const double *rhs, double *y, std::vector<int32
                 TRY(upload_mask(s, fin, s->fin_dev, st));
                 krylov_solve_y_kernel<<<gb, tb, 0, st>>>(s->ks, m, k + 1, B, s->fin_dev);
                 LDC_CHECK_LAUNCH();
-                TRY(vec_multi_axpy(s->Z, vs, k + 1, s->ks.yv, m, y, n, B, s->fin_dev, st));
+                TRY(vec_multi_axpy(s->Z, s->zs, k + 1, s->ks.yv, m, y, n, B, s->fin_dev, st));
                 for (int b = 0; b < B; ++b) if (fin[b]) run[b] = 0;
                 TRY(upload_mask(s, run, s->run_dev, st));
             }
@@ -690,7 +751,7 @@ static int fgmres(ldc_solver *s, const double *rhs, double *y, std::vector<int32
         // restart: fold the cycle into y, recompute the true residual
         krylov_solve_y_kernel<<<gb, tb, 0, st>>>(s->ks, m, k, B, s->run_dev);
         LDC_CHECK_LAUNCH();
-        TRY(vec_multi_axpy(s->Z, vs, k, s->ks.yv, m, y, n, B, s->run_dev, st));
+        TRY(vec_multi_axpy(s->Z, s->zs, k, s->ks.yv, m, y, n, B, s->run_dev, st));
         TRY(spmv_outer(s, y, rhs, s->rres, st));
         TRY(norm2_to(s, s->rres, s->ks.nrm2, s->run_dev, st));
         sqrt_kernel<<<gb, tb, 0, st>>>(s->ks.nrm2, s->ks.beta, B, s->run_dev);

@@ -62,7 +62,10 @@ int spmv_compact_launch(int nx, int ny, int batch, const double *Jc, const doubl
 
 // ---- precond.cu ----------------------------------------------------------------------------
 struct MgLevel {
-    int nx, ny;
+    int nx, ny;          // cells per row, rows HELD (a whole cavity, or the rows of this rank's strip)
+    // row-strip geometry of the level (a whole cavity: row_begin=0, ny_global=ny, no ghosts)
+    int row_begin, ny_global, v_rows;   // v_rows = held rows whose V is a real unknown
+    bool ghost_lo, ghost_hi;            // a strip below / above exists (vectors carry halo rows)
     double dx, dy;
     long N, n, nnz;
     double *X;       // state the level's Jacobian is linearised about   [batch*n]
@@ -72,7 +75,12 @@ struct MgLevel {
     double *dp;      // cell pressure corrections of the relaxation       [batch*N]
 };
 
+// Vectors of a level (X, x, b, r) are allocated with one spare row below and above the held rows;
+// for a strip those rows receive the neighbours' boundary rows (halo) before an operator reads them.
 int mg_restrict_state(const MgLevel &f, const MgLevel &c, int batch, cudaStream_t s);
+// the two relaxation kernels of a sweep on a given residual r (no SpMV)
+int mg_vanka_relax(const MgLevel &l, const double *r, double *x, bool assign, double om_u, double om_p,
+                   int batch, const int32_t *run, cudaStream_t s);
 int mg_extract_diag(const MgLevel &l, int batch, cudaStream_t s);
 // one damped additive cell-block relaxation sweep on level l: x += omega * B^{-1} (b - J x).
 // zero_guess: x is taken as 0 (skips the SpMV).
