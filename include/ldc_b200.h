@@ -115,6 +115,8 @@ typedef struct ldc_comm_ops {
                          int64_t row_count, void *stream);
     /* in-place all-reduce of device doubles; op 0 = sum, 1 = max */
     int (*allreduce)(void *ctx, double *buf_dev, int64_t count, int32_t op, void *stream);
+    /* in-place all-gather: rank r's `count` doubles sit at buf_dev + r*count on entry */
+    int (*allgather)(void *ctx, double *buf_dev, int64_t count, void *stream);
 } ldc_comm_ops;
 
 /* ---- device-resident Newton-Krylov solve of one pseudo-time step and the time stepper.

@@ -40,6 +40,8 @@ LDC_API int ldc_comm_halo_exchange(ldc_comm *c, double *first_owned_row_dev, int
                                    int64_t row_count, void *stream);
 /* in-place all-reduce of `count` doubles; op 0 = sum, 1 = max */
 LDC_API int ldc_comm_allreduce(ldc_comm *c, double *buf_dev, int64_t count, int32_t op, void *stream);
+/* in-place all-gather of `count` doubles per rank (rank r's piece at buf_dev + r*count) */
+LDC_API int ldc_comm_allgather(ldc_comm *c, double *buf_dev, int64_t count, void *stream);
 /* function table to hand to ldc_solver_set_comm */
 LDC_API const ldc_comm_ops *ldc_comm_get_ops(ldc_comm *c);
 

@@ -18,6 +18,7 @@ COMM_SYMBOLS = {
     'ldc_comm_last_error': (ctypes.c_char_p, []),
     'ldc_comm_halo_exchange': (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
     'ldc_comm_allreduce': (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
+    'ldc_comm_allgather': (ctypes.c_int, [_vp, _vp, _i64, _vp]),
     'ldc_comm_get_ops': (_vp, [_vp]),
 }
 _lib = None

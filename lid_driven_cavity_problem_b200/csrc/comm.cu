@@ -41,6 +41,11 @@ static int allreduce_cb(void *ctx, double *buf, int64_t count, int32_t op, void 
     return ldc_comm_allreduce((ldc_comm *)ctx, buf, count, op, stream);
 }
 
+static int allgather_cb(void *ctx, double *buf, int64_t count, void *stream)
+{
+    return ldc_comm_allgather((ldc_comm *)ctx, buf, count, stream);
+}
+
 extern "C" const char *ldc_comm_last_error(void) { return g_comm_error; }
 
 extern "C" int ldc_comm_unique_id(void *id_out)
@@ -73,6 +78,7 @@ extern "C" int ldc_comm_create(const void *id_bytes, int32_t nranks, int32_t ran
     c->ops.nranks = nranks;
     c->ops.halo_exchange = halo_cb;
     c->ops.allreduce = allreduce_cb;
+    c->ops.allgather = allgather_cb;
     *out = c;
     return LDC_OK;
 }
@@ -114,6 +120,15 @@ extern "C" int ldc_comm_allreduce(ldc_comm *c, double *buf, int64_t count, int32
     if (!c || !buf || count <= 0) return comm_fail("ldc_comm_allreduce", "bad arguments");
     if (c->nranks == 1) return LDC_OK;
     LDC_NCCL(ncclAllReduce(buf, buf, (size_t)count, ncclDouble, op == 1 ? ncclMax : ncclSum, c->comm,
+                           (cudaStream_t)stream));
+    return LDC_OK;
+}
+
+extern "C" int ldc_comm_allgather(ldc_comm *c, double *buf, int64_t count, void *stream)
+{
+    if (!c || !buf || count <= 0) return comm_fail("ldc_comm_allgather", "bad arguments");
+    if (c->nranks == 1) return LDC_OK;
+    LDC_NCCL(ncclAllGather(buf + (size_t)c->rank * count, buf, (size_t)count, ncclDouble, c->comm,
                            (cudaStream_t)stream));
     return LDC_OK;
 }

@@ -299,25 +299,47 @@ extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *op
     A(s->dalloc(&s->bc_dev, B));
     // multigrid hierarchy.  A strip coarsens its own rows; strip boundaries stay aligned because the
     // partition is a multiple of 2^levels rows (strip_partition).
-    int nlev = 1;
+    // A strip hierarchy is distributed on its fine levels and REPLICATED below: once a level is
+    // small (<= kRepCells cells in the whole grid) or the strip cannot be halved any more, its
+    // right-hand side is all-gathered and every rank continues the cycle on the full coarse grid.
+    // That keeps the latency-bound coarse levels free of halo exchanges and makes them identical to
+    // the single-GPU hierarchy.
+    const long kRepCells = 32768;
+    int nlev = 1, l_rep = -1;
     if (o.pc_type == LDC_PC_MG_VANKA) {
         int nx = g->nx, ny = g->row_count, rb = g->row_begin, nyg = g->ny;
         const int min_size = o.mg_min_size > 2 ? o.mg_min_size : 3;
-        const int min_rows = s->strip ? 2 : min_size;
-        while (nx % 2 == 0 && ny % 2 == 0 && rb % 2 == 0 && nyg % 2 == 0 && nx / 2 >= min_size &&
-               ny / 2 >= min_rows && (o.mg_levels <= 0 || nlev < o.mg_levels)) {
+        bool rep = false;
+        while ((o.mg_levels <= 0 || nlev < o.mg_levels) && nx % 2 == 0 && nyg % 2 == 0 && nx / 2 >= min_size) {
+            if (!rep) {
+                if (ny % 2 != 0 || rb % 2 != 0) break;
+                if (s->strip && ((long)(nx / 2) * (nyg / 2) <= kRepCells || ny / 2 < 2)) {
+                    if (ny / 2 < 1) break;
+                    rep = true;
+                    l_rep = nlev;
+                } else if (!s->strip && ny / 2 < min_size) break;
+            } else if (nyg / 2 < min_size) break;
             nx /= 2; ny /= 2; rb /= 2; nyg /= 2; ++nlev;
         }
     }
     s->levels.resize(nlev);
     for (int l = 0; l < nlev && rc == LDC_OK; ++l) {
         MgLevel &L = s->levels[l];
+        L.replicated = (l_rep >= 0 && l >= l_rep);
         L.nx = g->nx >> l;
-        L.ny = g->row_count >> l;
-        L.row_begin = g->row_begin >> l;
         L.ny_global = g->ny >> l;
-        L.ghost_lo = s->ghost_lo;
-        L.ghost_hi = s->ghost_hi;
+        L.slice_begin = g->row_begin >> l;
+        L.slice_rows = g->row_count >> l;
+        if (L.replicated) {
+            L.ny = L.ny_global;
+            L.row_begin = 0;
+            L.ghost_lo = L.ghost_hi = false;
+        } else {
+            L.ny = g->row_count >> l;
+            L.row_begin = g->row_begin >> l;
+            L.ghost_lo = s->ghost_lo;
+            L.ghost_hi = s->ghost_hi;
+        }
         L.v_rows = (L.row_begin + L.ny < L.ny_global) ? L.ny : L.ny_global - 1 - L.row_begin;
         if (L.v_rows < 0) L.v_rows = 0;
         L.dx = g->dx * (double)(1 << l);
@@ -419,12 +441,14 @@ extern "C" double *ldc_solver_state_dev(ldc_solver *s) { return s ? s->X : nullp
 
 extern "C" int ldc_solver_set_comm(ldc_solver *s, const ldc_comm_ops *ops)
 {
-    LDC_REQUIRE(s && ops && ops->halo_exchange && ops->allreduce, "ldc_solver_set_comm: incomplete function table");
+    LDC_REQUIRE(s && ops && ops->halo_exchange && ops->allreduce && ops->allgather,
+                "ldc_solver_set_comm: incomplete function table");
     LDC_REQUIRE(s->batch == 1, "a distributed solver holds one cavity");
     s->comm = *ops;
     s->has_comm = true;
-    // NCCL calls are not replayed from CUDA graphs in this version
-    s->use_graphs = false;
+    // NCCL point-to-point and all-reduce calls are stream-ordered and can be captured; the
+    // environment switch is an escape hatch
+    if (getenv("LDC_STRIP_NO_GRAPHS") != nullptr) s->use_graphs = false;
     return LDC_OK;
 }
 
@@ -513,9 +537,39 @@ static int comm_halo(ldc_solver *s, double *first_owned_row, cudaStream_t st)
 
 static int level_halo(ldc_solver *s, const MgLevel &L, double *first_owned_row, cudaStream_t st)
 {
-    if (!s->has_comm || s->comm.nranks <= 1) return LDC_OK;
+    if (!s->has_comm || s->comm.nranks <= 1 || L.replicated) return LDC_OK;
     if (s->comm.halo_exchange(s->comm.ctx, first_owned_row, 3L * L.nx, L.ny, st) != 0) {
         set_error("comm halo exchange failed");
+        return LDC_ERR_STATE;
+    }
+    return LDC_OK;
+}
+
+// this rank's rows of a replicated level, seen as a strip (for the transfer kernels)
+static MgLevel slice_view(const MgLevel &L)
+{
+    MgLevel v = L;
+    const long off = 3L * L.nx * L.slice_begin;
+    v.ny = L.slice_rows;
+    v.row_begin = L.slice_begin;
+    v.N = (long)L.nx * L.slice_rows;
+    v.n = 3 * v.N;
+    v.ghost_lo = L.slice_begin > 0;
+    v.ghost_hi = L.slice_begin + L.slice_rows < L.ny_global;
+    v.v_rows = (v.row_begin + v.ny < L.ny_global) ? v.ny : L.ny_global - 1 - v.row_begin;
+    if (v.v_rows < 0) v.v_rows = 0;
+    v.X = L.X + off;
+    v.x = L.x ? L.x + off : nullptr;
+    v.b = L.b ? L.b + off : nullptr;
+    return v;
+}
+
+// every rank has filled its slice of a replicated level vector: make it whole everywhere
+static int gather_level(ldc_solver *s, const MgLevel &L, double *vec, cudaStream_t st)
+{
+    if (!s->has_comm || s->comm.nranks <= 1) return LDC_OK;
+    if (s->comm.allgather(s->comm.ctx, vec, 3L * L.nx * L.slice_rows, st) != 0) {
+        set_error("comm all-gather failed");
         return LDC_ERR_STATE;
     }
     return LDC_OK;
@@ -545,7 +599,16 @@ static int build_hierarchy(ldc_solver *s, cudaStream_t st)
 {
     for (size_t l = 0; l < s->levels.size(); ++l) {
         MgLevel &L = s->levels[l];
-        if (l > 0) TRY(mg_restrict_state(s->levels[l - 1], L, s->batch, st));
+        if (l > 0) {
+            const MgLevel &Fl = s->levels[l - 1];
+            if (L.replicated && !Fl.replicated) {   // strip -> replicated: restrict own rows, gather
+                const MgLevel view = slice_view(L);
+                TRY(mg_restrict_state(Fl, view, s->batch, st));
+                TRY(gather_level(s, L, L.X, st));
+            } else {
+                TRY(mg_restrict_state(Fl, L, s->batch, st));
+            }
+        }
         TRY(level_halo(s, L, L.X, st));   // a strip's Jacobian rows read the neighbours' boundary rows
         ldc_grid gl = level_grid(s, L);
         TRY(fd_jacobian_launch(&gl, L.X, s->U_old, s->V_old, nullptr, L.J, st));
@@ -570,7 +633,7 @@ static int sweep(ldc_solver *s, const MgLevel &L, const double *b, double *x, bo
 // x_P -= mean(x_P) over the WHOLE level (all strips)
 static int remove_mean(ldc_solver *s, const MgLevel &L, double *x, const int32_t *run, cudaStream_t st)
 {
-    if (!s->strip) return mg_remove_mean_pressure(L, x, s->batch, run, s->partials, s->ks.hcol2, st);
+    if (!s->strip || L.replicated) return mg_remove_mean_pressure(L, x, s->batch, run, s->partials, s->ks.hcol2, st);
     TRY(mg_pressure_sum(L, x, 1, run, s->partials, s->ks.hcol2, st));
     TRY(comm_allreduce(s, s->ks.hcol2, 1, 0, st));
     return mg_subtract_mean(L, x, 1, run, s->ks.hcol2, (long)L.nx * L.ny_global, st);
@@ -597,10 +660,21 @@ static int vcycle(ldc_solver *s, size_t l, const double *b, double *x, const int
     TRY(level_spmv(s, L, x, b, L.r, run, st));
     const MgLevel &C = s->levels[l + 1];
     TRY(level_halo(s, L, L.r, st));   // the last coarse V row of a strip reads the fine row above it
-    TRY(mg_restrict_residual(L, L.r, C, C.b, s->batch, run, st));
-    TRY(vcycle(s, l + 1, C.b, C.x, run, st));
-    TRY(level_halo(s, C, C.x, st));   // the first fine V row of a strip interpolates from below
-    TRY(mg_prolong_add(C, C.x, L, x, s->batch, run, st));
+    if (C.replicated && !L.replicated) {
+        // distributed -> replicated: every rank restricts into its rows of the coarse right-hand
+        // side, one all-gather makes it whole, the rest of the cycle runs without communication,
+        // and each rank interpolates from its own rows (+ the row below) of the coarse correction
+        const MgLevel view = slice_view(C);
+        TRY(mg_restrict_residual(L, L.r, view, view.b, s->batch, run, st));
+        TRY(gather_level(s, C, C.b, st));
+        TRY(vcycle(s, l + 1, C.b, C.x, run, st));
+        TRY(mg_prolong_add(view, view.x, L, x, s->batch, run, st));
+    } else {
+        TRY(mg_restrict_residual(L, L.r, C, C.b, s->batch, run, st));
+        TRY(vcycle(s, l + 1, C.b, C.x, run, st));
+        TRY(level_halo(s, C, C.x, st));   // the first fine V row of a strip interpolates from below
+        TRY(mg_prolong_add(C, C.x, L, x, s->batch, run, st));
+    }
     for (int k = 0; k < s->opt.pc_sweeps; ++k) TRY(sweep(s, L, b, x, false, run, st));
     return LDC_OK;
 }

@@ -66,6 +66,10 @@ struct MgLevel {
     // row-strip geometry of the level (a whole cavity: row_begin=0, ny_global=ny, no ghosts)
     int row_begin, ny_global, v_rows;   // v_rows = held rows whose V is a real unknown
     bool ghost_lo, ghost_hi;            // a strip below / above exists (vectors carry halo rows)
+    // coarse levels of a distributed hierarchy are REPLICATED: every rank holds the whole (small)
+    // level and works on it without communication; slice_* is this rank's share of its rows
+    bool replicated;
+    int slice_begin, slice_rows;
     double dx, dy;
     long N, n, nnz;
     double *X;       // state the level's Jacobian is linearised about   [batch*n]

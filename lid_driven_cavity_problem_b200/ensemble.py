@@ -187,8 +187,14 @@ class CudaEnsembleSolver(object):
         return ts
 
 
+def interleaved(n_items, world_size, rank):
+    """indices rank, rank+world, ...: when cavities are sorted by difficulty (Reynolds number) every
+    rank gets the same mix, which balances the lock-step batches"""
+    return list(range(rank, n_items, world_size))
+
+
 def run_ensemble(graphs, final_time=None, minimum_dt=1e-6, adaptative_dt=True, max_steps=None,
-                 distributed=False, **solver_options):
+                 distributed=False, interleave=False, **solver_options):
     """Solve every cavity of ``graphs``.  With ``distributed=True`` (torch.distributed initialised,
     one process per GPU) each rank solves ``partition(len(graphs), world, rank)`` and the per-cavity
     summaries are gathered on every rank; there is no collective on the data path.
@@ -197,8 +203,12 @@ def run_ensemble(graphs, final_time=None, minimum_dt=1e-6, adaptative_dt=True, m
     if distributed:
         import torch.distributed as dist
         rank, world = dist.get_rank(), dist.get_world_size()
-    mine = partition(len(graphs), world, rank)
-    local = graphs[mine]
+    if interleave:
+        mine_idx = interleaved(len(graphs), world, rank)
+    else:
+        sl = partition(len(graphs), world, rank)
+        mine_idx = list(range(len(graphs))[sl])
+    local = [graphs[i] for i in mine_idx]
     summaries, fields = [], None
     if len(local) > 0:
         solver = CudaEnsembleSolver(local, **solver_options)
@@ -207,7 +217,7 @@ def run_ensemble(graphs, final_time=None, minimum_dt=1e-6, adaptative_dt=True, m
         counters = solver.counters() if hasattr(solver, 'counters') else {}
         run_ensemble.last_counters = dict(counters, sweeps=int((ts.steps + ts.retries).max()))
         for b in range(len(local)):
-            summaries.append(dict(index=mine.start + b, bc=float(local[b].bc), status=int(ts.status[b]),
+            summaries.append(dict(index=mine_idx[b], bc=float(local[b].bc), status=int(ts.status[b]),
                                   t=float(ts.t[b]), dt=float(ts.dt[b]), steps=int(ts.steps[b]),
                                   retries=int(ts.retries[b]), newton=int(solver.newton_iterations[b]),
                                   krylov=int(solver.krylov_iterations[b]), rank=rank))
@@ -216,5 +226,5 @@ def run_ensemble(graphs, final_time=None, minimum_dt=1e-6, adaptative_dt=True, m
         import torch.distributed as dist
         gathered = [None] * world
         dist.all_gather_object(gathered, summaries)
-        summaries = [s for part in gathered for s in part]
+        summaries = sorted((s for part in gathered for s in part), key=lambda d: d['index'])
     return summaries, fields

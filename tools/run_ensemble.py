@@ -23,6 +23,7 @@ def main():
     ap.add_argument('--re-min', type=float, default=100.0)
     ap.add_argument('--re-max', type=float, default=10000.0)
     ap.add_argument('--max-steps', type=int, default=None)
+    ap.add_argument('--interleave', action='store_true', help='deal cavities round-robin to the ranks')
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -40,7 +41,7 @@ def main():
     if world > 1:
         dist.barrier()
     t0 = time.time()
-    summ, _ = run_ensemble(graphs, max_steps=args.max_steps, distributed=world > 1)
+    summ, _ = run_ensemble(graphs, max_steps=args.max_steps, distributed=world > 1, interleave=args.interleave)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
