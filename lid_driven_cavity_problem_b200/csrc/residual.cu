@@ -19,6 +19,8 @@
 //                           registers.  Each X value is loaded once per tile (+1 halo row), the
 //                           4 divisions + ~80 flops per cell are half of the cell kernel's, and
 //                           sum(F^2) is reduced by warp shuffles for the Newton norm.
+#include <stdlib.h>
+
 #include "ldc_internal.cuh"
 
 namespace ldc {
@@ -690,18 +692,27 @@ static MarchPlan plan_march(const ldc_grid &g)
 {
     const int col_warps = (g.nx + kMarchCols - 1) / kMarchCols;
     const int col_blocks = (col_warps + kMarchWarps - 1) / kMarchWarps;
-    // aim at >= 2 blocks of 128 threads per resident slot (148 SMs x 4 blocks) so the tail is
-    // short, while keeping tiles tall enough to amortise the halo row.
-    const long target_blocks = 2L * 4 * sm_count();
-    long row_tiles = (target_blocks + (long)col_blocks * g.batch - 1) / ((long)col_blocks * g.batch);
-    if (row_tiles < 1) row_tiles = 1;
-    int rows = (int)((g.row_count + row_tiles - 1) / row_tiles);
-    if (rows < 8) rows = 8;
-    if (rows > 64) rows = 64;
-    if (rows > g.row_count) rows = g.row_count;
+    // Rows per tile: a tile costs rows + ~2.5 rows (halo row + pipeline fill), so tall tiles are
+    // cheaper, but the blocks should fill the resident slots (4 blocks of 128 threads per SM at
+    // ~108 registers) in whole waves.  Pick the candidate with the best product of the two.
+    const long slots = 4L * sm_count();
+    int best_rows = g.row_count < 8 ? g.row_count : 8;
+    double best = -1.0;
+    const char *env = getenv("LDC_MARCH_ROWS");
+    if (env && atoi(env) > 0) {
+        best_rows = atoi(env) < g.row_count ? atoi(env) : g.row_count;
+    } else {
+        for (int rows = 8; rows <= 64 && rows <= g.row_count; ++rows) {
+            const long blocks = (long)col_blocks * ((g.row_count + rows - 1) / rows) * g.batch;
+            const long waves = (blocks + slots - 1) / slots;
+            const double balance = (double)blocks / (double)(waves * slots);
+            const double score = balance * (double)rows / ((double)rows + 2.5);
+            if (score > best) { best = score; best_rows = rows; }
+        }
+    }
     MarchPlan pl;
-    pl.rows_per_tile = rows;
-    pl.grid = dim3(col_blocks, (g.row_count + rows - 1) / rows, g.batch);
+    pl.rows_per_tile = best_rows;
+    pl.grid = dim3(col_blocks, (g.row_count + best_rows - 1) / best_rows, g.batch);
     return pl;
 }
 

@@ -39,13 +39,19 @@ def _pinned(name, n, torch):
     return buf
 
 
-def _to_device(name, host, n, torch):
-    """host array -> device tensor through a cached pinned buffer"""
+def _as_f64(name, host, n):
     arr = np.ascontiguousarray(host, dtype=np.float64).reshape(-1)
     if arr.size != n:
         raise ValueError("%s has %d entries, expected %d" % (name, arr.size, n))
+    return arr
+
+
+def _to_device(name, host, n, torch):
+    """host array -> device tensor: multi-threaded copy into a cached pinned buffer, then an
+    asynchronous DMA on the current stream (the next array is staged while this one travels)"""
+    arr = _as_f64(name, host, n)
     pin = _pinned(name, n, torch)
-    pin.numpy()[:] = arr
+    pin.copy_(torch.from_numpy(arr))
     return pin.to('cuda', non_blocking=True)
 
 
@@ -82,8 +88,12 @@ def residual_function(X, graph):
     nx, ny = int(graph.pressure_mesh.nx), int(graph.pressure_mesh.ny)
     n = 3 * nx * ny
     X_dev = _to_device('X', X, n, torch)
-    F_dev = residual_function_device(X_dev, graph)
+    U_old_dev = _to_device('U_old', graph.ns_x_mesh.phi_old, (nx - 1) * ny, torch)
+    V_old_dev = _to_device('V_old', graph.ns_y_mesh.phi_old, nx * (ny - 1), torch)
+    F_dev = residual_function_device(X_dev, graph, U_old_dev=U_old_dev, V_old_dev=V_old_dev)
     out = _pinned('F', n, torch)
     out.copy_(F_dev, non_blocking=True)
+    result = np.empty(n, dtype=np.float64)      # freshly allocated, like the reference backends
     torch.cuda.current_stream().synchronize()
-    return out.numpy().copy()
+    torch.from_numpy(result).copy_(out)         # multi-threaded host copy out of the pinned buffer
+    return result
