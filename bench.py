@@ -202,6 +202,95 @@ def time_to_converge(max_seconds=120.0):
             "pseudo_time": steps[-1] if steps else 0.0}
 
 
+def _time_loop(fn, n_sets, iters, warmup=3):
+    import torch
+    for k in range(warmup):
+        fn(k % n_sets)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(iters):
+        fn(k % n_sets)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def named_sizes_table(peak):
+    """residual kernel on every grid BASELINE.json names (kernel-only, CUDA events, L2-cold by
+    rotating buffer sets): Mcells/s and fraction of the HBM roofline at 8*(8N-nx-ny) bytes."""
+    import torch
+    from lid_driven_cavity_problem_b200 import _native
+    lib = _native.lib()
+    st = _native.current_stream()
+    rows = []
+    for nx, ny, batch in [(100, 100, 1), (256, 256, 1), (1024, 1024, 1), (64, 64, 512), (4096, 4096, 1)]:
+        g, X = synthetic_case(nx, ny)
+        N = nx * ny
+        bytes_alg = 8 * (8 * N - nx - ny) * batch
+        n_sets = max(2, min(12, int(700e6 // bytes_alg) + 1))
+        Xd = torch.from_numpy(np.tile(X, batch)).cuda()
+        Xs = [Xd + float(k) for k in range(n_sets)]
+        Fs = [torch.empty_like(Xd) for _ in range(n_sets)]
+        Us = [torch.from_numpy(np.tile(g.ns_x_mesh.phi_old, batch)).cuda() for _ in range(n_sets)]
+        Vs = [torch.from_numpy(np.tile(g.ns_y_mesh.phi_old, batch)).cuda() for _ in range(n_sets)]
+        grid = _native.grid_from_graph(g, batch=batch)
+
+        def run(k):
+            lib.ldc_residual(grid, _native.ptr(Xs[k]), _native.ptr(Us[k]), _native.ptr(Vs[k]), _native.ptr(Fs[k]),
+                             None, None, 0, st)
+        ms = _time_loop(run, n_sets, 60 if N * batch < 4e6 else 20)
+        gbs = bytes_alg / ms / 1e6
+        rows.append({"grid": "%dx%d" % (nx, ny) + (" x%d" % batch if batch > 1 else ""), "kernel_ms": round(ms, 5),
+                     "mcells_per_s": round(N * batch / ms / 1e3, 1), "gb_per_s": round(gbs, 1),
+                     "frac_of_hbm_peak": round(gbs / peak, 4)})
+        del Xs, Fs, Us, Vs, Xd
+        torch.cuda.empty_cache()
+    return rows
+
+
+def spmv_table(peak, n=1024):
+    """SpMV on the 1024^2 Jacobian: the solver's compact layout (own bytes 26*8+48 per cell) and the
+    canonical CSR over the reference mask (12*nnz + 4(n+1) + 16n bytes)."""
+    import torch
+    from lid_driven_cavity_problem_b200 import _native
+    from lid_driven_cavity_problem_b200.nonlinear_solver import _common
+    lib = _native.lib()
+    st = _native.current_stream()
+    g, X = synthetic_case(n, n)
+    N = n * n
+    grid = _native.grid_from_graph(g)
+    Xd = torch.from_numpy(X).cuda()
+    Ud = torch.from_numpy(g.ns_x_mesh.phi_old).cuda()
+    Vd = torch.from_numpy(g.ns_y_mesh.phi_old).cuda()
+    nnz = int(lib.ldc_mask_nnz(n, n, 3))
+    sets = 3
+    Jc = [torch.empty(26 * N, dtype=torch.float64, device='cuda') for _ in range(sets)]
+    Jm = [torch.empty(nnz, dtype=torch.float64, device='cuda') for _ in range(2)]
+    for j in Jc:
+        lib.ldc_fd_jacobian_compact(grid, _native.ptr(Xd), _native.ptr(Ud), _native.ptr(Vd), _native.ptr(j), st)
+    for j in Jm:
+        lib.ldc_fd_jacobian(grid, _native.ptr(Xd), _native.ptr(Ud), _native.ptr(Vd), _native.ptr(j), st)
+    xs = [torch.randn(3 * N, dtype=torch.float64, device='cuda') for _ in range(sets)]
+    ys = [torch.empty(3 * N, dtype=torch.float64, device='cuda') for _ in range(sets)]
+    indptr, indices = _common.jacobian_mask_device(n, n, 3)
+    ms_c = _time_loop(lambda k: lib.ldc_spmv_compact(grid, _native.ptr(Jc[k]), _native.ptr(xs[k]), _native.ptr(ys[k]), st), sets, 30)
+    ms_m = _time_loop(lambda k: lib.ldc_spmv_csr(3 * N, _native.ptr(indptr), _native.ptr(indices), _native.ptr(Jm[k % 2]),
+                                                 _native.ptr(xs[k]), _native.ptr(ys[k]), st), sets, 20)
+    ms_fd = _time_loop(lambda k: lib.ldc_fd_jacobian(grid, _native.ptr(Xd), _native.ptr(Ud), _native.ptr(Vd),
+                                                     _native.ptr(Jm[k % 2]), st), 2, 10)
+    own = (26 * 8 + 48) * N
+    canon = 12 * nnz + 4 * (3 * N + 1) + 16 * 3 * N
+    fd_bytes = 8 * (8 * N - 2 * n) - 24 * N + 8 * nnz
+    return {"grid": "%dx%d" % (n, n),
+            "spmv_compact": {"ms": round(ms_c, 5), "bytes": own, "gb_per_s": round(own / ms_c / 1e6, 1),
+                             "frac_of_hbm_peak": round(own / ms_c / 1e6 / peak, 4)},
+            "spmv_csr_canonical": {"ms": round(ms_m, 5), "bytes": canon, "gb_per_s": round(canon / ms_m / 1e6, 1),
+                                   "frac_of_hbm_peak": round(canon / ms_m / 1e6 / peak, 4)},
+            "fd_jacobian_csr": {"ms": round(ms_fd, 5), "bytes": fd_bytes, "gb_per_s": round(fd_bytes / ms_fd / 1e6, 1),
+                                "frac_of_hbm_peak": round(fd_bytes / ms_fd / 1e6 / peak, 4)}}
+
+
 def cpu_solve_sample(budget=25.0):
     """Bounded sample of the reference path for the solve (PETSc-equivalent restatement, PETSc is
     not installable): one FD Jacobian + ILU(0) + a few GMRES(30) iterations of the FIRST Newton
@@ -240,6 +329,7 @@ def main():
     ap.add_argument('--impl', default='cuda')
     ap.add_argument('--no-solve', action='store_true', help='skip the time-to-converge run')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline legs')
+    ap.add_argument('--no-tables', action='store_true', help='skip the per-size / per-kernel tables')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)
@@ -405,6 +495,12 @@ def main():
     if not args.no_cpu:
         v, cores, kind, sample, best = cpu_reference_residual()
         line["cpu_baseline"] = {"value": v, "unit": "Mcells/s", "cores": cores, "kind": kind, "sample": sample}
+    if world == 1 and not args.no_tables:
+        try:
+            line["named_sizes"] = named_sizes_table(peak)
+            line["other_kernels"] = spmv_table(peak)
+        except Exception as e:
+            line["named_sizes"] = {"error": repr(e)}
     if world == 1 and not args.no_solve:
         try:
             line["time_to_converge"] = time_to_converge()
