@@ -484,7 +484,11 @@ def main():
                        n_sets, n_sets * res_bytes / 1e6),
                    "kernel": "residual_march_kernel (flux form, bit-exact arithmetic)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                     "frac": achieved / peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
+                     # (profiles/r1b_residual_march_ncu.csv): reads equal the algorithmic 41.9 MB, the
+                     # 25 MB of F stay in the 126 MB L2 within one launch
+                     "traffic": 43364608 if (NX, NY) == (1024, 1024) else None, "peak_kind": peak_kind,
                      "algorithmic_bytes_per_launch": res_bytes, "kernel_ms": kern_ms},
         "e2e": {"value": NX * NY * world / e2e_s / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_call": e2e_s * 1e3,
