@@ -130,7 +130,7 @@ typedef struct ldc_solver_options {
     double snes_divtol;                       /* 1e4: ||F|| > divtol*||F0|| -> reason -9 (PETSc default) */
     int32_t snes_max_it;                      /* 50 */
     int32_t snes_max_funcs;                   /* 10000 (PETSc default) */
-    double ksp_rtol, ksp_atol, ksp_dtol;      /* 1e-5, 1e-50, 1e5 (PETSc KSP defaults) */
+    double ksp_rtol, ksp_atol, ksp_dtol;      /* 1e-3 (PETSc: 1e-5), 1e-50, 1e5 */
     int32_t ksp_max_it;                       /* 150 (PETSc: 10000 with ILU) */
     int32_t gmres_restart;                    /* 30 */
     int32_t pc_type;                          /* LDC_PC_* */
