@@ -20,6 +20,7 @@
 //                           4 divisions + ~80 flops per cell are half of the cell kernel's, and
 //                           sum(F^2) is reduced by warp shuffles for the Newton norm.
 #include <stdlib.h>
+#include <string.h>
 
 #include "ldc_internal.cuh"
 
@@ -336,15 +337,20 @@ residual_march_kernel(const ldc_grid g, const double *__restrict__ X,
                       const double *__restrict__ U_old, const double *__restrict__ V_old,
                       double *__restrict__ F, double *__restrict__ partials, int rows_per_tile)
 {
+    // Programmatic dependent launch: let the next kernel of the stream start launching while this
+    // one runs (its blocks take the SM slots ours free up), and do not touch global memory before
+    // every kernel queued ahead of us has completed.  Without the launch attribute both are no-ops.
+    asm volatile("griddepcontrol.launch_dependents;");
     const int inst = blockIdx.z;
     const Strides st = instance_strides(g);
     X += inst * st.x;
     F += inst * st.x;
     U_old += inst * st.u;
     V_old += inst * st.v;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const Phys p = make_phys(g, inst);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i_first = blockIdx.x * kMarchWarps * kMarchCols - 1;   // column of lane 0, warp 0
     const int i = i_first + warp * kMarchCols + lane;
     const int jl0 = blockIdx.y * rows_per_tile;
@@ -803,9 +809,23 @@ extern "C" int ldc_residual(const ldc_grid *g, const double *X_dev, const double
         // FAST needs exact unit density/viscosity; per-instance dt/bc do not matter
         const bool fast = pow2 && g->rho == 1.0 && g->mi == 1.0;
         const dim3 blk(kMarchWarps * 32);
-#define LDC_LAUNCH_MARCH(P2, FA, CD)                                                     \
-    residual_march_kernel<P2, FA, CD><<<pl.grid, blk, 0, s>>>(*g, X_dev, U_old_dev, V_old_dev, \
-                                                             F_dev, partials, pl.rows_per_tile)
+        // launched with programmatic stream serialization so that back-to-back evaluations overlap
+        // their launch latency and tails (see the griddepcontrol pair in the kernel)
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = pl.grid;
+        cfg.blockDim = blk;
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = (getenv("LDC_NO_PDL") == nullptr) ? 1 : 0;
+        const int rows_arg = pl.rows_per_tile;
+#define LDC_LAUNCH_MARCH(P2, FA, CD)                                                                  \
+    LDC_CUDA(cudaLaunchKernelEx(&cfg, residual_march_kernel<P2, FA, CD>, *g, X_dev, U_old_dev, V_old_dev, \
+                                F_dev, partials, rows_arg))
         if (g->use_cds) {
             if (fast) LDC_LAUNCH_MARCH(true, true, true);
             else if (pow2) LDC_LAUNCH_MARCH(true, false, true);
