@@ -74,7 +74,7 @@ struct MgLevel {
     long N, n, nnz;
     double *X;       // state the level's Jacobian is linearised about   [batch*n]
     double *J;       // compact Jacobian Jc[26][N] (jacobian.cu)            [batch*26*N]
-    double *diag;    // diagonal of J                                     [batch*n]
+    double *diag;    // INVERSE diagonal of J (0 for continuity rows)     [batch*n]
     double *x, *b, *r;  // correction, right-hand side, residual          [batch*n]
     double *dp;      // cell pressure corrections of the relaxation       [batch*N]
 };
