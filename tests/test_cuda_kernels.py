@@ -52,7 +52,7 @@ def test_golden_random_cases_bit_exact(cuda, golden):
 
 
 @pytest.mark.parametrize("nx,ny", [(100, 100), (256, 256), (257, 131), (1024, 1024), (61, 1030), (124, 9),
-                                   (126, 40), (250, 33), (4, 3), (2048, 64)])
+                                   (126, 40), (250, 33), (4, 3), (2048, 64), (4096, 4096)])
 def test_residual_vs_oracle(cuda, nx, ny):
     from oracle import ldc_oracle as orc
     g, X = synthetic_case(nx, ny)
@@ -152,7 +152,8 @@ def test_mask_bit_exact(cuda, golden):
 
 
 @pytest.mark.parametrize("nx,ny,bc", [(9, 8, 100.0), (13, 9, 400.0), (4, 3, 10.0), (64, 64, 1000.0),
-                                      (100, 100, 1000.0), (131, 77, 3200.0)])
+                                      (100, 100, 1000.0), (131, 77, 3200.0), (256, 256, 1000.0),
+                                      (1024, 1024, 3200.0)])
 def test_fd_jacobian_vs_oracle(cuda, nx, ny, bc):
     from oracle import ldc_oracle as orc
     torch, native = cuda['torch'], cuda['native']
@@ -294,3 +295,32 @@ def test_compact_jacobian_and_spmv_row_strips(cuda):
         yl = torch.empty(3 * nx * rows, dtype=torch.float64, device='cuda')
         native.check(lib.ldc_spmv_compact(sg, native.ptr(Jl), xl.data_ptr() + off, native.ptr(yl), st))
         assert np.array_equal(yl.cpu().numpy(), yfull[3 * nx * j0:3 * nx * j1]), (j0, j1)
+
+
+def test_ensemble_512x64_residual_full_size(cuda):
+    """BASELINE config 4 at full size: 512 cavities of 64x64, Re log-spaced 100..10000, one launch"""
+    from oracle import ldc_oracle as orc
+    torch, native = cuda['torch'], cuda['native']
+    B, n = 512, 64
+    bcs = 100.0 * 100.0 ** (np.arange(B) / (B - 1))
+    Xs, Us, Vs, Fs = [], [], [], []
+    for b in range(B):
+        g, X = synthetic_case(n, n, bc=float(bcs[b]), seed=b)
+        Xs.append(X); Us.append(g.ns_x_mesh.phi_old); Vs.append(g.ns_y_mesh.phi_old)
+        Fs.append(orc.residual_function(X, g))
+    g, _ = synthetic_case(n, n)
+    grid = native.grid_from_graph(g, batch=B)
+    bc_dev = torch.from_numpy(bcs).cuda()
+    grid.bc_dev = bc_dev.data_ptr()
+    Xd = torch.from_numpy(np.concatenate(Xs)).cuda()
+    Ud = torch.from_numpy(np.concatenate(Us)).cuda()
+    Vd = torch.from_numpy(np.concatenate(Vs)).cuda()
+    F = torch.empty_like(Xd)
+    n2 = torch.zeros(B, dtype=torch.float64, device='cuda')
+    work = torch.empty(int(native.lib().ldc_residual_work_doubles(grid)), dtype=torch.float64, device='cuda')
+    native.check(native.lib().ldc_residual(grid, native.ptr(Xd), native.ptr(Ud), native.ptr(Vd), native.ptr(F),
+                                           native.ptr(n2), native.ptr(work), 0, native.current_stream()))
+    Fh = F.cpu().numpy()
+    assert np.array_equal(Fh, np.concatenate(Fs))
+    ref_n2 = np.array([np.dot(f, f) for f in Fs])
+    assert np.abs(n2.cpu().numpy() - ref_n2).max() <= 1e-12 * ref_n2.max()
