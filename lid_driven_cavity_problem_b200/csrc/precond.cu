@@ -400,17 +400,6 @@ int mg_vanka_relax(const MgLevel &l, const double *r, double *x, bool assign, do
     return LDC_OK;
 }
 
-int mg_vanka_sweep(const MgLevel &l, const double *b, double *x, bool zero_guess, double om_u,
-                   double om_p, int batch, const int32_t *run, cudaStream_t s)
-{
-    const double *r = b;
-    if (!zero_guess) {
-        if (int rc = spmv_compact_launch(l.nx, l.ny, batch, l.J, x, b, l.r, run, s)) return rc;
-        r = l.r;
-    }
-    return mg_vanka_relax(l, r, x, zero_guess, om_u, om_p, batch, run, s);
-}
-
 int mg_restrict_residual(const MgLevel &f, const double *r_f, const MgLevel &c, double *b_c,
                          int batch, const int32_t *run, cudaStream_t s)
 {

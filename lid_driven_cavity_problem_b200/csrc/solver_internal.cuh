@@ -86,10 +86,6 @@ int mg_restrict_state(const MgLevel &f, const MgLevel &c, int batch, cudaStream_
 int mg_vanka_relax(const MgLevel &l, const double *r, double *x, bool assign, double om_u, double om_p,
                    int batch, const int32_t *run, cudaStream_t s);
 int mg_extract_diag(const MgLevel &l, int batch, cudaStream_t s);
-// one damped additive cell-block relaxation sweep on level l: x += omega * B^{-1} (b - J x).
-// zero_guess: x is taken as 0 (skips the SpMV).
-int mg_vanka_sweep(const MgLevel &l, const double *b, double *x, bool zero_guess, double om_u,
-                   double om_p, int batch, const int32_t *run, cudaStream_t s);
 int mg_restrict_residual(const MgLevel &f, const double *r_f, const MgLevel &c, double *b_c,
                          int batch, const int32_t *run, cudaStream_t s);
 // x_P -= mean(x_P) per instance; partials/sums are scratch (>= batch*ceil(N/2048) and batch doubles)
