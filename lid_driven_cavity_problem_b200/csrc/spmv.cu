@@ -125,8 +125,12 @@ spmv_mask_kernel(int nx, int ny, long nnz, const double *__restrict__ values,
 // store is contiguous.  208 + 48 B/cell instead of 504 + 48.  Used by the Krylov solver and
 // the multigrid smoother (same numbers as the CSR product: the dropped entries are exact zeros).
 // ---------------------------------------------------------------------------------------------
-static constexpr int kCmpCells = 256;
-static constexpr int kCmpLo = 0, kCmpMid = 3 * 257, kCmpHi = 3 * (257 + 258), kCmpXs = 3 * (257 + 258 + 257);
+#ifndef LDC_CMP_CELLS
+#define LDC_CMP_CELLS 128
+#endif
+static constexpr int kCmpCells = LDC_CMP_CELLS;
+static constexpr int kCmpLo = 0, kCmpMid = 3 * (kCmpCells + 1), kCmpHi = 3 * (2 * kCmpCells + 3),
+                     kCmpXs = 3 * (3 * kCmpCells + 4);
 
 __global__ void __launch_bounds__(kCmpCells)
 spmv_compact_kernel(int nx, int ny, const double *__restrict__ Jc, const double *__restrict__ x,
