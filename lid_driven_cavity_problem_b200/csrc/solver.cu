@@ -305,7 +305,8 @@ extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *op
     // right-hand side is all-gathered and every rank continues the cycle on the full coarse grid.
     // That keeps the latency-bound coarse levels free of halo exchanges and makes them identical to
     // the single-GPU hierarchy.
-    const long kRepCells = 32768;
+    long kRepCells = 32768;
+    if (const char *env = getenv("LDC_REP_CELLS")) kRepCells = atol(env) > 0 ? atol(env) : kRepCells;
     int nlev = 1, l_rep = -1;
     if (o.pc_type == LDC_PC_MG_VANKA) {
         int nx = g->nx, ny = g->row_count, rb = g->row_begin, nyg = g->ny;
@@ -775,6 +776,14 @@ static int fgmres(ldc_solver *s, const double *rhs, double *y, std::vector<int32
     const ldc_solver_options &o = s->opt;
     const int tb = 64, gb = (B + tb - 1) / tb;
 
+    // A grid that cannot be coarsened (odd size) only has the single-level relaxation as
+    // preconditioner, whose iteration count grows with the grid; the fail-fast limit tuned for the
+    // multigrid cycle would turn every such solve into a spurious "diverged".
+    int ksp_max_it = o.ksp_max_it;
+    if (s->levels.size() == 1 && o.pc_type != LDC_PC_NONE) {
+        const int single = 10 * (s->g.nx + s->g.ny);
+        if (ksp_max_it < single) ksp_max_it = single;
+    }
     reason.assign(B, 0);
     its.assign(B, 0);
     relres.assign(B, 0.0);
@@ -810,7 +819,7 @@ static int fgmres(ldc_solver *s, const double *rhs, double *y, std::vector<int32
                 else if (r <= o.ksp_atol) rs = 3;
                 else if (r <= o.ksp_rtol * bnorm[b]) rs = 2;
                 else if (r >= o.ksp_dtol * bnorm[b]) rs = -4;
-                else if (its[b] >= o.ksp_max_it) rs = -3;
+                else if (its[b] >= ksp_max_it) rs = -3;
                 if (rs != 0) { reason[b] = rs; fin[b] = 1; any_fin = true; }
             }
             if (any_fin) {

@@ -71,7 +71,8 @@ def test_linear_solve_vs_direct():
             lib.ldc_solver_destroy(h)
 
 
-@pytest.mark.parametrize("nx,ny,bc", [(32, 32, 100.0), (64, 64, 1000.0), (40, 24, 400.0), (15, 15, 10.0)])
+@pytest.mark.parametrize("nx,ny,bc", [(32, 32, 100.0), (64, 64, 1000.0), (40, 24, 400.0), (15, 15, 10.0),
+                                      (33, 20, 100.0), (100, 38, 400.0), (3, 2, 10.0)])
 def test_one_step_converged_state_parity(nx, ny, bc):
     """north_star: converged U/V/P agree to 1e-8 relative (P up to its constant)."""
     from oracle import ldc_oracle as orc
