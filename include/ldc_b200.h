@@ -131,6 +131,7 @@ typedef struct ldc_solver_options {
     int32_t snes_max_it;                      /* 50 */
     int32_t snes_max_funcs;                   /* 10000 (PETSc default) */
     double ksp_rtol, ksp_atol, ksp_dtol;      /* 1e-3 (PETSc: 1e-5), 1e-50, 1e5 */
+    double ksp_stagnation;                    /* 0.9: a restart cycle leaving > 90% of the residual = failed solve */
     int32_t ksp_max_it;                       /* 150 (PETSc: 10000 with ILU) */
     int32_t gmres_restart;                    /* 30 */
     int32_t pc_type;                          /* LDC_PC_* */

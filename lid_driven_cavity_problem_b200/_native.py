@@ -29,7 +29,7 @@ class LdcSolverOptions(ctypes.Structure):
                 ('snes_stol', ctypes.c_double), ('snes_divtol', ctypes.c_double),
                 ('snes_max_it', ctypes.c_int32), ('snes_max_funcs', ctypes.c_int32),
                 ('ksp_rtol', ctypes.c_double), ('ksp_atol', ctypes.c_double),
-                ('ksp_dtol', ctypes.c_double),
+                ('ksp_dtol', ctypes.c_double), ('ksp_stagnation', ctypes.c_double),
                 ('ksp_max_it', ctypes.c_int32), ('gmres_restart', ctypes.c_int32),
                 ('pc_type', ctypes.c_int32), ('pc_sweeps', ctypes.c_int32),
                 ('mg_levels', ctypes.c_int32), ('mg_coarse_sweeps', ctypes.c_int32),

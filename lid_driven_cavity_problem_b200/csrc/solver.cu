@@ -221,6 +221,7 @@ extern "C" void ldc_solver_default_options(ldc_solver_options *o)
                             // PETSc's default 1e-5 costs 25-35% more Krylov work for the same Newton path
     o->ksp_atol = 1e-50;
     o->ksp_dtol = 1e5;
+    o->ksp_stagnation = 0.9;
     o->ksp_max_it = 150;    // PETSc: 10000 (ILU).  A multigrid-preconditioned solve that needs more is a
                             // Newton step about to diverge: failing fast (-> dt halving) is 1.4-2x cheaper
     o->gmres_restart = 30;
@@ -787,6 +788,8 @@ static int fgmres(ldc_solver *s, const double *rhs, double *y, std::vector<int32
     reason.assign(B, 0);
     its.assign(B, 0);
     relres.assign(B, 0.0);
+    std::vector<double> cycle_start(B, 1.0);   // relative residual at the start of the restart cycle
+    if (getenv("LDC_DEBUG_KSP")) fprintf(stderr, "[ksp] new solve bnorm=%.3e\n", bnorm[0]);
     for (int b = 0; b < B; ++b)
         if (run[b] && !(bnorm[b] > 0.0)) { run[b] = 0; reason[b] = (bnorm[b] == 0.0) ? 3 : -9; }
     TRY(upload_mask(s, run, s->run_dev, st));
@@ -830,6 +833,20 @@ static int fgmres(ldc_solver *s, const double *rhs, double *y, std::vector<int32
                 for (int b = 0; b < B; ++b) if (fin[b]) run[b] = 0;
                 TRY(upload_mask(s, run, s->run_dev, st));
             }
+        }
+        if (getenv("LDC_DEBUG_KSP")) fprintf(stderr, "[ksp] cycle end: its=%d relres=%.3e\n", its[0], relres[0]);
+        // Stagnation: a full restart cycle that removes less than 10% of the residual will not reach
+        // the tolerance within the iteration cap (seen when the Newton iterate has blown up: relres
+        // 0.92 -> 0.92 -> 0.92 ...); healthy cycles reduce it by 4x or more.  Failing now instead of
+        // at ksp_max_it is the same outcome (reason -3 -> Newton diverged -> dt halved), 4 cycles sooner.
+        {
+            bool changed = false;
+            for (int b = 0; b < B; ++b) {
+                if (!run[b]) continue;
+                if (relres[b] > o.ksp_stagnation * cycle_start[b]) { reason[b] = -3; run[b] = 0; changed = true; }
+                cycle_start[b] = relres[b];
+            }
+            if (changed && any(run)) TRY(upload_mask(s, run, s->run_dev, st));
         }
         if (!any(run)) break;
         // restart: fold the cycle into y, recompute the true residual
