@@ -142,6 +142,8 @@ typedef struct ldc_solver_options {
     int32_t residual_variant;                 /* as in ldc_residual */
     int32_t gmres_refine;                     /* 1: second Gram-Schmidt pass (CGS2); 0: PETSc's default (never) */
     int32_t use_cuda_graphs;                  /* 1: replay each Krylov iteration as one CUDA graph */
+    int32_t pc_fp32;                          /* 1: run the multigrid cycle (a preconditioner only) in fp32 */
+    int32_t reserved;
     double pc_omega_u, pc_omega_p;            /* damping of the cell-block relaxation */
 } ldc_solver_options;
 

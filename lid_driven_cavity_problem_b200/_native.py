@@ -35,6 +35,7 @@ class LdcSolverOptions(ctypes.Structure):
                 ('mg_levels', ctypes.c_int32), ('mg_coarse_sweeps', ctypes.c_int32),
                 ('mg_min_size', ctypes.c_int32), ('residual_variant', ctypes.c_int32),
                 ('gmres_refine', ctypes.c_int32), ('use_cuda_graphs', ctypes.c_int32),
+                ('pc_fp32', ctypes.c_int32), ('reserved', ctypes.c_int32),
                 ('pc_omega_u', ctypes.c_double), ('pc_omega_p', ctypes.c_double)]
 
 

@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "solver_internal.cuh"
@@ -168,6 +169,7 @@ struct ldc_solver {
     cudaEvent_t ev_in;
     // row-strip decomposition
     bool strip, ghost_lo, ghost_hi, has_comm;
+    bool mixed;   // multigrid cycle in fp32 (non-distributed solvers)
     ldc_comm_ops comm;
     int v_rows;
     double *X_alloc, *xpad_alloc, *xpad;
@@ -227,6 +229,7 @@ extern "C" void ldc_solver_default_options(ldc_solver_options *o)
     o->gmres_restart = 30;
     o->gmres_refine = 0;    // PETSc's default (classical Gram-Schmidt, never refine)
     o->use_cuda_graphs = 1;
+    o->pc_fp32 = 1;
     o->pc_type = LDC_PC_MG_VANKA;
     o->pc_sweeps = 2;
     o->mg_levels = 0;
@@ -270,6 +273,7 @@ extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *op
     s->ghost_lo = g->row_begin > 0;
     s->ghost_hi = g->row_begin + g->row_count < g->ny;
     s->has_comm = false;
+    s->mixed = (o.pc_fp32 != 0) && !s->strip && o.pc_type != LDC_PC_NONE;
     memset(&s->comm, 0, sizeof(s->comm));
     s->v_rows = (g->row_begin + g->row_count < g->ny ? g->row_count : g->ny - 1 - g->row_begin);
     if (s->v_rows < 0) s->v_rows = 0;
@@ -371,6 +375,15 @@ extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *op
         A(s->dalloc(&L.diag, (size_t)B * L.n));
         A(padded(&L.r));
         A(s->dalloc(&L.dp, (size_t)B * L.N));
+        L.Jf = L.diagf = L.xf = L.bf = L.rf = L.dpf = nullptr;
+        if (s->mixed) {
+            A(s->dalloc(&L.Jf, (size_t)B * 26 * L.N));
+            A(s->dalloc(&L.diagf, (size_t)B * L.n));
+            A(s->dalloc(&L.xf, (size_t)B * L.n));
+            A(s->dalloc(&L.bf, (size_t)B * L.n));
+            A(s->dalloc(&L.rf, (size_t)B * L.n));
+            A(s->dalloc(&L.dpf, (size_t)B * L.N));
+        }
     }
     // Krylov workspace
     A(s->dalloc(&s->V, (size_t)(m + 1) * B * n));
@@ -578,13 +591,36 @@ static int gather_level(ldc_solver *s, const MgLevel &L, double *vec, cudaStream
     return LDC_OK;
 }
 
+// typed views of a level's arrays
+template <typename T> struct Lv;
+template <> struct Lv<double> {
+    static const double *J(const MgLevel &l) { return l.J; }
+    static const double *idiag(const MgLevel &l) { return l.diag; }
+    static double *x(const MgLevel &l) { return l.x; }
+    static double *b(const MgLevel &l) { return l.b; }
+    static double *r(const MgLevel &l) { return l.r; }
+    static double *dp(const MgLevel &l) { return l.dp; }
+};
+template <> struct Lv<float> {
+    static const float *J(const MgLevel &l) { return l.Jf; }
+    static const float *idiag(const MgLevel &l) { return l.diagf; }
+    static float *x(const MgLevel &l) { return l.xf; }
+    static float *b(const MgLevel &l) { return l.bf; }
+    static float *r(const MgLevel &l) { return l.rf; }
+    static float *dp(const MgLevel &l) { return l.dpf; }
+};
+
+static int level_halo_t(ldc_solver *s, const MgLevel &L, double *v, cudaStream_t st) { return level_halo(s, L, v, st); }
+static int level_halo_t(ldc_solver *, const MgLevel &, float *, cudaStream_t) { return LDC_OK; }  // fp32 cycles are never distributed
+
 // y = J_l x or b - J_l x with the true rows of level l; x must be a padded vector (its halo rows
 // are refreshed here for a strip)
-static int level_spmv(ldc_solver *s, const MgLevel &L, double *x_padded, const double *b, double *y,
-                      const int32_t *run, cudaStream_t st)
+template <typename T>
+static int level_spmv(ldc_solver *s, const MgLevel &L, T *x_padded, const T *b, T *y, const int32_t *run,
+                      cudaStream_t st)
 {
-    TRY(level_halo(s, L, x_padded, st));
-    return spmv_compact_launch(L.nx, L.ny, s->batch, L.J, x_padded, b, y, run, st, L.ghost_lo, L.ghost_hi);
+    TRY(level_halo_t(s, L, x_padded, st));
+    return spmv_compact_launch<T>(L.nx, L.ny, s->batch, Lv<T>::J(L), x_padded, b, y, run, st, L.ghost_lo, L.ghost_hi);
 }
 
 // same for an unpadded x (copied into the padded scratch first; strips only)
@@ -592,9 +628,9 @@ static int spmv_outer(ldc_solver *s, const double *x, const double *b, double *y
 {
     const MgLevel &L0 = s->levels[0];
     if (!s->strip)
-        return spmv_compact_launch(L0.nx, L0.ny, s->batch, L0.J, x, b, y, s->run_dev, st);
+        return spmv_compact_launch<double>(L0.nx, L0.ny, s->batch, L0.J, x, b, y, s->run_dev, st);
     TRY(vec_copy(x, s->xpad, s->n, 1, nullptr, st));
-    return level_spmv(s, L0, s->xpad, b, y, s->run_dev, st);
+    return level_spmv<double>(s, L0, s->xpad, b, y, s->run_dev, st);
 }
 
 // Jacobian at the current state on every level + diagonals
@@ -622,28 +658,33 @@ static int build_hierarchy(ldc_solver *s, cudaStream_t st)
 
 // one relaxation sweep x += omega B^-1 (b - J x); the residual uses the true operator (halo of x),
 // the cell-block solves are local to the strip
-static int sweep(ldc_solver *s, const MgLevel &L, const double *b, double *x, bool zero_guess,
-                 const int32_t *run, cudaStream_t st)
+template <typename T>
+static int sweep(ldc_solver *s, const MgLevel &L, const T *b, T *x, bool zero_guess, const int32_t *run,
+                 cudaStream_t st)
 {
-    const double *r = b;
+    const T *r = b;
     if (!zero_guess) {
-        TRY(level_spmv(s, L, x, b, L.r, run, st));
-        r = L.r;
+        TRY(level_spmv<T>(s, L, x, b, Lv<T>::r(L), run, st));
+        r = Lv<T>::r(L);
     }
-    return mg_vanka_relax(L, r, x, zero_guess, s->opt.pc_omega_u, s->opt.pc_omega_p, s->batch, run, st);
+    return mg_vanka_relax<T>(L, r, Lv<T>::idiag(L), Lv<T>::dp(L), x, zero_guess, s->opt.pc_omega_u,
+                             s->opt.pc_omega_p, s->batch, run, st);
 }
 
 // x_P -= mean(x_P) over the WHOLE level (all strips)
-static int remove_mean(ldc_solver *s, const MgLevel &L, double *x, const int32_t *run, cudaStream_t st)
+template <typename T>
+static int remove_mean(ldc_solver *s, const MgLevel &L, T *x, const int32_t *run, cudaStream_t st)
 {
-    if (!s->strip || L.replicated) return mg_remove_mean_pressure(L, x, s->batch, run, s->partials, s->ks.hcol2, st);
-    TRY(mg_pressure_sum(L, x, 1, run, s->partials, s->ks.hcol2, st));
+    if (!s->strip || L.replicated)
+        return mg_remove_mean_pressure<T>(L, x, s->batch, run, s->partials, s->ks.hcol2, st);
+    TRY(mg_pressure_sum<T>(L, x, 1, run, s->partials, s->ks.hcol2, st));
     TRY(comm_allreduce(s, s->ks.hcol2, 1, 0, st));
-    return mg_subtract_mean(L, x, 1, run, s->ks.hcol2, (long)L.nx * L.ny_global, st);
+    return mg_subtract_mean<T>(L, x, 1, run, s->ks.hcol2, (long)L.nx * L.ny_global, st);
 }
 
-// x must be a padded vector of level l
-static int vcycle(ldc_solver *s, size_t l, const double *b, double *x, const int32_t *run, cudaStream_t st)
+// x must be a padded vector of level l (fp32 cycles: plain vectors, never distributed)
+template <typename T>
+static int vcycle(ldc_solver *s, size_t l, const T *b, T *x, const int32_t *run, cudaStream_t st)
 {
     const MgLevel &L = s->levels[l];
     if (l + 1 == s->levels.size()) {
@@ -655,30 +696,31 @@ static int vcycle(ldc_solver *s, size_t l, const double *b, double *x, const int
             const int side = L.nx > L.ny_global ? L.nx : L.ny_global;
             if (sweeps < 2 * side) sweeps = 2 * side;
         }
-        for (int k = 0; k < sweeps; ++k) TRY(sweep(s, L, b, x, k == 0, run, st));
-        if (s->levels.size() > 1) TRY(remove_mean(s, L, x, run, st));
+        for (int k = 0; k < sweeps; ++k) TRY(sweep<T>(s, L, b, x, k == 0, run, st));
+        if (s->levels.size() > 1) TRY(remove_mean<T>(s, L, x, run, st));
         return LDC_OK;
     }
-    for (int k = 0; k < s->opt.pc_sweeps; ++k) TRY(sweep(s, L, b, x, k == 0, run, st));
-    TRY(level_spmv(s, L, x, b, L.r, run, st));
+    for (int k = 0; k < s->opt.pc_sweeps; ++k) TRY(sweep<T>(s, L, b, x, k == 0, run, st));
+    T *r = Lv<T>::r(L);
+    TRY(level_spmv<T>(s, L, x, b, r, run, st));
     const MgLevel &C = s->levels[l + 1];
-    TRY(level_halo(s, L, L.r, st));   // the last coarse V row of a strip reads the fine row above it
+    TRY(level_halo_t(s, L, r, st));   // the last coarse V row of a strip reads the fine row above it
     if (C.replicated && !L.replicated) {
-        // distributed -> replicated: every rank restricts into its rows of the coarse right-hand
-        // side, one all-gather makes it whole, the rest of the cycle runs without communication,
-        // and each rank interpolates from its own rows (+ the row below) of the coarse correction
+        // distributed -> replicated (fp64 only): every rank restricts into its rows of the coarse
+        // right-hand side, one all-gather makes it whole, the rest of the cycle runs without
+        // communication, and each rank interpolates from its own rows (+ the row below)
         const MgLevel view = slice_view(C);
-        TRY(mg_restrict_residual(L, L.r, view, view.b, s->batch, run, st));
+        TRY(mg_restrict_residual<T>(L, r, view, Lv<T>::b(view), s->batch, run, st));
         TRY(gather_level(s, C, C.b, st));
-        TRY(vcycle(s, l + 1, C.b, C.x, run, st));
-        TRY(mg_prolong_add(view, view.x, L, x, s->batch, run, st));
+        TRY(vcycle<T>(s, l + 1, Lv<T>::b(C), Lv<T>::x(C), run, st));
+        TRY(mg_prolong_add<T>(view, Lv<T>::x(view), L, x, s->batch, run, st));
     } else {
-        TRY(mg_restrict_residual(L, L.r, C, C.b, s->batch, run, st));
-        TRY(vcycle(s, l + 1, C.b, C.x, run, st));
-        TRY(level_halo(s, C, C.x, st));   // the first fine V row of a strip interpolates from below
-        TRY(mg_prolong_add(C, C.x, L, x, s->batch, run, st));
+        TRY(mg_restrict_residual<T>(L, r, C, Lv<T>::b(C), s->batch, run, st));
+        TRY(vcycle<T>(s, l + 1, Lv<T>::b(C), Lv<T>::x(C), run, st));
+        TRY(level_halo_t(s, C, Lv<T>::x(C), st));   // the first fine V row of a strip interpolates from below
+        TRY(mg_prolong_add<T>(C, Lv<T>::x(C), L, x, s->batch, run, st));
     }
-    for (int k = 0; k < s->opt.pc_sweeps; ++k) TRY(sweep(s, L, b, x, false, run, st));
+    for (int k = 0; k < s->opt.pc_sweeps; ++k) TRY(sweep<T>(s, L, b, x, false, run, st));
     return LDC_OK;
 }
 
@@ -686,11 +728,21 @@ static int vcycle(ldc_solver *s, size_t l, const double *b, double *x, const int
 static int apply_pc(ldc_solver *s, const double *v, double *z, const int32_t *run, cudaStream_t st)
 {
     if (s->opt.pc_type == LDC_PC_NONE) return vec_copy(v, z, s->n, s->batch, run, st);
-    TRY(vcycle(s, 0, v, z, run, st));
     // The Jacobian is singular by the constant-pressure mode (with finite-difference
     // noise: nearly singular).  Searching only among zero-mean pressure corrections keeps the
     // Krylov solution out of that mode (what KSPSetNullSpace does in PETSc).
-    return remove_mean(s, s->levels[0], z, run, st);
+    if (s->mixed) {
+        // the cycle is only a preconditioner of the flexible GMRES: run it in fp32 (half the bytes
+        // on its bandwidth-bound levels); the Krylov vectors, the operator and every norm stay fp64
+        const MgLevel &L0 = s->levels[0];
+        const long n = (long)s->batch * s->n;
+        TRY((vec_convert<double, float>(v, L0.bf, n, st)));
+        TRY(vcycle<float>(s, 0, L0.bf, L0.xf, run, st));
+        TRY(remove_mean<float>(s, L0, L0.xf, run, st));
+        return vec_convert<float, double>(L0.xf, z, n, st);
+    }
+    TRY(vcycle<double>(s, 0, v, z, run, st));
+    return remove_mean<double>(s, s->levels[0], z, run, st);
 }
 
 // squared norm of x per instance -> dst_dev[b]
@@ -715,7 +767,7 @@ static int krylov_iteration_body(ldc_solver *s, int k, cudaStream_t st)
     const int tb = 64, gb = (B + tb - 1) / tb;
     double *vk = s->V + (long)k * vs, *zk = s->Z + (long)k * s->zs;
     TRY(apply_pc(s, vk, zk, s->run_dev, st));
-    TRY(level_spmv(s, L0, zk, nullptr, s->w, s->run_dev, st));
+    TRY(level_spmv<double>(s, L0, zk, nullptr, s->w, s->run_dev, st));
     TRY(vec_multi_dot(s->V, vs, k + 1, s->w, n, B, s->run_dev, s->partials, st));
     TRY(vec_reduce_partials(s->partials, k + 1, nblk, B, s->ks.hcol, st));
     TRY(comm_allreduce(s, s->ks.hcol, (long)B * (k + 1), 0, st));

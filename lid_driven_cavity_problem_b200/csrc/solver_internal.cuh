@@ -56,9 +56,9 @@ int spmv_mask_launch(int nx, int ny, int batch, const double *values, const doub
                      const double *b, double *y, const int32_t *run, cudaStream_t s);
 // same on the compact layout Jc[26][N] (see jacobian.cu)
 // ny = rows of the block of cells; ghost_lo/ghost_hi: x carries valid halo rows below/above
-int spmv_compact_launch(int nx, int ny, int batch, const double *Jc, const double *x,
-                        const double *b, double *y, const int32_t *run, cudaStream_t s,
-                        bool ghost_lo = false, bool ghost_hi = false);
+template <typename T>
+int spmv_compact_launch(int nx, int ny, int batch, const T *Jc, const T *x, const T *b, T *y,
+                        const int32_t *run, cudaStream_t s, bool ghost_lo = false, bool ghost_hi = false);
 
 // ---- precond.cu ----------------------------------------------------------------------------
 struct MgLevel {
@@ -77,25 +77,36 @@ struct MgLevel {
     double *diag;    // INVERSE diagonal of J (0 for continuity rows)     [batch*n]
     double *x, *b, *r;  // correction, right-hand side, residual          [batch*n]
     double *dp;      // cell pressure corrections of the relaxation       [batch*N]
+    // fp32 twins for the mixed-precision cycle (nullptr when the solver runs the cycle in fp64)
+    float *Jf, *diagf, *xf, *bf, *rf, *dpf;
 };
 
 // Vectors of a level (X, x, b, r) are allocated with one spare row below and above the held rows;
 // for a strip those rows receive the neighbours' boundary rows (halo) before an operator reads them.
+// The relaxation / transfer wrappers are templates on the scalar type: the multigrid cycle of a
+// non-distributed solver runs in fp32 (it is only a preconditioner of the flexible GMRES, which
+// stays in fp64), halving the traffic of its bandwidth-bound levels.
 int mg_restrict_state(const MgLevel &f, const MgLevel &c, int batch, cudaStream_t s);
-// the two relaxation kernels of a sweep on a given residual r (no SpMV)
-int mg_vanka_relax(const MgLevel &l, const double *r, double *x, bool assign, double om_u, double om_p,
-                   int batch, const int32_t *run, cudaStream_t s);
 int mg_extract_diag(const MgLevel &l, int batch, cudaStream_t s);
-int mg_restrict_residual(const MgLevel &f, const double *r_f, const MgLevel &c, double *b_c,
-                         int batch, const int32_t *run, cudaStream_t s);
-// x_P -= mean(x_P) per instance; partials/sums are scratch (>= batch*ceil(N/2048) and batch doubles)
-int mg_remove_mean_pressure(const MgLevel &l, double *x, int batch, const int32_t *run,
-                            double *partials, double *sums, cudaStream_t s);
-int mg_pressure_sum(const MgLevel &l, const double *x, int batch, const int32_t *run,
-                    double *partials, double *sums, cudaStream_t s);
-int mg_subtract_mean(const MgLevel &l, double *x, int batch, const int32_t *run, const double *sums,
-                     long n_cells_global, cudaStream_t s);
-int mg_prolong_add(const MgLevel &c, const double *x_c, const MgLevel &f, double *x_f, int batch,
+template <typename A, typename B> int vec_convert(const A *in, B *out, long n, cudaStream_t s);
+template <typename T>
+int mg_vanka_relax(const MgLevel &l, const T *r, const T *idiag, T *dp, T *x, bool assign, double om_u,
+                   double om_p, int batch, const int32_t *run, cudaStream_t s);
+template <typename T>
+int mg_restrict_residual(const MgLevel &f, const T *r_f, const MgLevel &c, T *b_c, int batch,
+                         const int32_t *run, cudaStream_t s);
+template <typename T>
+int mg_prolong_add(const MgLevel &c, const T *x_c, const MgLevel &f, T *x_f, int batch,
                    const int32_t *run, cudaStream_t s);
+// x_P -= mean(x_P) per instance; partials/sums are scratch (>= batch*ceil(N/2048) and batch doubles)
+template <typename T>
+int mg_remove_mean_pressure(const MgLevel &l, T *x, int batch, const int32_t *run, double *partials,
+                            double *sums, cudaStream_t s);
+template <typename T>
+int mg_pressure_sum(const MgLevel &l, const T *x, int batch, const int32_t *run, double *partials,
+                    double *sums, cudaStream_t s);
+template <typename T>
+int mg_subtract_mean(const MgLevel &l, T *x, int batch, const int32_t *run, const double *sums,
+                     long n_cells_global, cudaStream_t s);
 
 }  // namespace ldc

@@ -132,17 +132,18 @@ static constexpr int kCmpCells = LDC_CMP_CELLS;
 static constexpr int kCmpLo = 0, kCmpMid = 3 * (kCmpCells + 1), kCmpHi = 3 * (2 * kCmpCells + 3),
                      kCmpXs = 3 * (3 * kCmpCells + 4);
 
+template <typename T>
 __global__ void __launch_bounds__(kCmpCells)
-spmv_compact_kernel(int nx, int ny, const double *__restrict__ Jc, const double *__restrict__ x,
-                    const double *__restrict__ rhs, double *__restrict__ y,
+spmv_compact_kernel(int nx, int ny, const T *__restrict__ Jc, const T *__restrict__ x,
+                    const T *__restrict__ rhs, T *__restrict__ y,
                     const int32_t *__restrict__ run, int ghost_lo, int ghost_hi)
 {
     // ny = rows of this block of cells (a whole cavity or a row strip).  For a strip, x points at
     // the first owned row and ghost_lo / ghost_hi say whether the row below / above it holds valid
     // halo data; without them the product is the strip's diagonal block (block-Jacobi).
     if (run && !run[blockIdx.y]) return;
-    __shared__ double xs[kCmpXs];
-    __shared__ double ys[3 * kCmpCells];
+    __shared__ T xs[kCmpXs];
+    __shared__ T ys[3 * kCmpCells];
     const long N = (long)nx * ny;
     const int inst = blockIdx.y;
     Jc += (long)inst * 26 * N;
@@ -155,13 +156,13 @@ spmv_compact_kernel(int nx, int ny, const double *__restrict__ Jc, const double 
     const long cell_lo = ghost_lo ? -(long)nx : 0, cell_hi = N + (ghost_hi ? nx : 0);
 
     // coefficient loads first: they are independent of the staging below
-    double J[26];
+    T J[26];
     if (c < N) {
 #pragma unroll
         for (int k = 0; k < 26; ++k) J[k] = __ldg(Jc + (long)k * N + c);
     } else {
 #pragma unroll
-        for (int k = 0; k < 26; ++k) J[k] = 0.0;
+        for (int k = 0; k < 26; ++k) J[k] = (T)0;
     }
     for (int t = tid; t < kCmpXs; t += kCmpCells) {
         long cell;
@@ -169,18 +170,18 @@ spmv_compact_kernel(int nx, int ny, const double *__restrict__ Jc, const double 
         if (t < kCmpMid) { cell = c0 - nx + t / 3; e = t % 3; }
         else if (t < kCmpHi) { cell = c0 - 1 + (t - kCmpMid) / 3; e = (t - kCmpMid) % 3; }
         else { cell = c0 + nx - 1 + (t - kCmpHi) / 3; e = (t - kCmpHi) % 3; }
-        xs[t] = (cell >= cell_lo && cell < cell_hi) ? __ldg(x + 3 * cell + e) : 0.0;
+        xs[t] = (cell >= cell_lo && cell < cell_hi) ? __ldg(x + 3 * cell + e) : (T)0;
     }
     __syncthreads();
     {
-        const double *lo = xs + kCmpLo + 3 * tid;     // cell c-nx   (lo[3..5] = c-nx+1)
-        const double *mi = xs + kCmpMid + 3 * tid;    // cell c-1    (mi[3..5] = c, mi[6..8] = c+1)
-        const double *hi = xs + kCmpHi + 3 * tid;     // cell c+nx-1 (hi[3..5] = c+nx)
-        double s0 = J[0] * lo[2];
+        const T *lo = xs + kCmpLo + 3 * tid;     // cell c-nx   (lo[3..5] = c-nx+1)
+        const T *mi = xs + kCmpMid + 3 * tid;    // cell c-1    (mi[3..5] = c, mi[6..8] = c+1)
+        const T *hi = xs + kCmpHi + 3 * tid;     // cell c+nx-1 (hi[3..5] = c+nx)
+        T s0 = J[0] * lo[2];
         s0 = fma(J[1], mi[1], s0);
         s0 = fma(J[2], mi[4], s0);
         s0 = fma(J[3], mi[5], s0);
-        double s1 = J[4] * lo[1];
+        T s1 = J[4] * lo[1];
         s1 = fma(J[5], lo[2], s1);
         s1 = fma(J[6], lo[5], s1);
         s1 = fma(J[7], mi[1], s1);
@@ -191,7 +192,7 @@ spmv_compact_kernel(int nx, int ny, const double *__restrict__ Jc, const double 
         s1 = fma(J[12], mi[7], s1);
         s1 = fma(J[13], mi[8], s1);
         s1 = fma(J[14], hi[4], s1);
-        double s2 = J[15] * lo[2];
+        T s2 = J[15] * lo[2];
         s2 = fma(J[16], mi[1], s2);
         s2 = fma(J[17], mi[2], s2);
         s2 = fma(J[18], mi[3], s2);
@@ -264,16 +265,20 @@ int spmv_mask_launch(int nx, int ny, int batch, const double *values, const doub
     LDC_CHECK_LAUNCH();
     return LDC_OK;
 }
-int spmv_compact_launch(int nx, int ny, int batch, const double *Jc, const double *x,
-                        const double *b, double *y, const int32_t *run, cudaStream_t s,
-                        bool ghost_lo, bool ghost_hi)
+template <typename T>
+int spmv_compact_launch(int nx, int ny, int batch, const T *Jc, const T *x, const T *b, T *y,
+                        const int32_t *run, cudaStream_t s, bool ghost_lo, bool ghost_hi)
 {
     const long N = (long)nx * ny;
     dim3 grid((unsigned)((N + kCmpCells - 1) / kCmpCells), batch);
-    spmv_compact_kernel<<<grid, kCmpCells, 0, s>>>(nx, ny, Jc, x, b, y, run, ghost_lo ? 1 : 0, ghost_hi ? 1 : 0);
+    spmv_compact_kernel<T><<<grid, kCmpCells, 0, s>>>(nx, ny, Jc, x, b, y, run, ghost_lo ? 1 : 0, ghost_hi ? 1 : 0);
     LDC_CHECK_LAUNCH();
     return LDC_OK;
 }
+template int spmv_compact_launch<double>(int, int, int, const double *, const double *, const double *, double *,
+                                         const int32_t *, cudaStream_t, bool, bool);
+template int spmv_compact_launch<float>(int, int, int, const float *, const float *, const float *, float *,
+                                        const int32_t *, cudaStream_t, bool, bool);
 }  // namespace ldc
 
 using namespace ldc;
@@ -284,7 +289,7 @@ extern "C" int ldc_spmv_compact(const ldc_grid *g, const double *compact_dev, co
     if (int rc = validate_grid(g, false)) return rc;
     LDC_REQUIRE(compact_dev && x_dev && y_dev && x_dev != y_dev, "ldc_spmv_compact: bad device pointers");
     // row strip: x_dev points at the first owned row, halo rows (if the strip has neighbours) around it
-    return spmv_compact_launch(g->nx, g->row_count, g->batch, compact_dev, x_dev, nullptr, y_dev, nullptr,
+    return spmv_compact_launch<double>(g->nx, g->row_count, g->batch, compact_dev, x_dev, nullptr, y_dev, nullptr,
                                (cudaStream_t)stream, g->row_begin > 0, g->row_begin + g->row_count < g->ny);
 }
 

@@ -54,3 +54,16 @@ def test_product_never_imports_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.cpp', '.h')):
                 text = open(os.path.join(root, f)).read()
                 assert 'ldc_oracle' not in text and 'from oracle' not in text, os.path.join(root, f)
+
+
+def test_option_struct_layout_and_defaults():
+    """ctypes mirror of ldc_solver_options: same size as the C struct (checked through the defaults
+    the library writes) and the documented defaults"""
+    import ctypes
+    from lid_driven_cavity_problem_b200 import _native
+    o = _native.LdcSolverOptions()
+    _native.load_library().ldc_solver_default_options(ctypes.byref(o))
+    assert (o.snes_rtol, o.snes_atol, o.snes_stol, o.snes_max_it) == (1e-4, 1e-4, 1e-4, 50)   # petsc_solver_wrapper.py:135
+    assert o.gmres_restart == 30 and o.pc_type == _native.PC_MG_VANKA
+    assert o.pc_omega_u == 0.8 and o.pc_omega_p == 0.8      # last fields: a layout slip would garble them
+    assert ctypes.sizeof(_native.LdcGrid) == 88 and ctypes.sizeof(_native.LdcNewtonReport) == 56
