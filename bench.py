@@ -107,18 +107,34 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _use_all_host_threads(reexec=False):
+    """torchrun exports OMP_NUM_THREADS=1 to its workers, but the CPU arms are meant to use every
+    host core.  libgomp reads the variable once at load time (resetting the count later through
+    omp_set_num_threads measured slower here), so the reference arm re-executes itself with the
+    variable corrected before anything is loaded.  Returns the thread count in effect."""
+    cores = os.cpu_count() or 1
+    cur = os.environ.get('OMP_NUM_THREADS', '')
+    if reexec and cur.strip() not in ('', str(cores)) and not os.environ.get('LDC_BENCH_REEXEC'):
+        env = dict(os.environ, OMP_NUM_THREADS=str(cores), LDC_BENCH_REEXEC='1')
+        sys.stdout.flush()
+        os.execve(sys.executable, [sys.executable] + sys.argv, env)
+    try:
+        return int(cur) if cur.strip() else cores
+    except ValueError:
+        return cores
+
+
 def cpu_reference_residual(seconds_budget=12.0, nx=NX, ny=NY):
     """reference C++-OpenMP residual through its pybind11 entry (the reference path, Python
     overhead included), all host threads; returns (Mcells/s best-of-N, cores, kind, sample)."""
     from oracle import ldc_oracle as orc
-    cores = os.cpu_count() or 1
-    os.environ.setdefault('OMP_NUM_THREADS', str(cores))
     g, X = synthetic_case(nx, ny)
     try:
         ref = orc.ref_module()
         fn, kind = (lambda: ref.residual_function_omp(X, g)), 'reference'
     except Exception:
         fn, kind = (lambda: orc.residual_function(X, g, nthreads=0)), 'port'
+    cores = _use_all_host_threads()
     fn()
     times, t_start = [], time.time()
     while time.time() - t_start < seconds_budget and len(times) < 200:
@@ -137,14 +153,13 @@ def run_reference_arm(args):
         return
     warm, steps = max(args.warmup, 1), max(args.steps, 1)
     from oracle import ldc_oracle as orc
-    cores = os.cpu_count() or 1
-    os.environ.setdefault('OMP_NUM_THREADS', str(cores))
     g, X = synthetic_case(NX, NY)
     try:
         ref = orc.ref_module()
         fn, kind = (lambda: ref.residual_function_omp(X, g)), 'reference'
     except Exception:
         fn, kind = (lambda: orc.residual_function(X, g, nthreads=0)), 'port'
+    cores = _use_all_host_threads()
     for _ in range(warm):
         fn()
     t0 = time.perf_counter()
@@ -332,6 +347,8 @@ def main():
     ap.add_argument('--no-tables', action='store_true', help='skip the per-size / per-kernel tables')
     args = ap.parse_args()
     if args.impl == 'reference':
+        if int(os.environ.get('RANK', '0')) == 0:
+            _use_all_host_threads(reexec=True)
         run_reference_arm(args)
         return
 
