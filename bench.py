@@ -8,7 +8,9 @@ time-to-converge of the 1024x1024 Re=1000 steady solve (extra key ``time_to_conv
 One *step* = one residual evaluation F(X) of a 1024x1024 cavity per GPU on the synthetic inputs of
 SURVEY 8(d), inputs resident in HBM, L2-cold by rotating through buffer sets whose total size is
 several times the 126 MB L2.  With N > 1 GPUs the global grid is 1024 x (1024*N), decomposed into
-row strips (one per rank) with a one-row halo exchange per evaluation (weak scaling).
+row strips (one per rank); the one-row halos are read from the neighbour GPUs' peer-mapped memory
+inside the residual kernel (ldc_residual_peer: flag handshake, one launch, no collective; the
+NCCL send/recv + kernel variant is timed next to it under ``halo``).  Weak scaling.
 ``e2e`` is the same evaluation through the reference-facing plug-in
 ``cuda_residual_function.residual_function(X_numpy, graph)``: host buffers in, host buffer out,
 host<->device copies inside the timed region.
@@ -379,8 +381,18 @@ def main():
     res_bytes = 8 * (8 * N - nx - ny_local)
     n_sets = 9  # 9 x 67 MB = 604 MB of inputs+outputs in rotation >> 126 MB L2
     row = 3 * nx
-    # each set: [ghost row below | owned rows | ghost row above]
-    Xbuf = [torch.zeros(row * (ny_local + 2), dtype=torch.float64, device='cuda') for _ in range(n_sets)]
+    # each set: [ghost row below | owned rows | ghost row above].  With N > 1 the sets live in one
+    # peer-mapped region per rank (CUDA IPC, lid_driven_cavity_problem_b200/peer_halo.py) so that
+    # the neighbour strips' kernels can read the boundary rows directly over NVLink.
+    peer_strip = None
+    if world > 1:
+        from lid_driven_cavity_problem_b200 import peer_halo
+        region = comm.peer_alloc(peer_halo.region_bytes(nx, ny_local, n_sets))
+        Xbuf = [torch.as_tensor(peer_halo._DeviceSpan(region[0] + peer_halo.HEADER_BYTES +
+                                                      k * 8 * row * (ny_local + 2), row * (ny_local + 2)),
+                                device='cuda') for k in range(n_sets)]
+    else:
+        Xbuf = [torch.zeros(row * (ny_local + 2), dtype=torch.float64, device='cuda') for _ in range(n_sets)]
     for k in range(n_sets):
         Xbuf[k][row:row * (ny_local + 1)] = torch.from_numpy(X).cuda() + float(k)
     Fs = [torch.empty(3 * N, dtype=torch.float64, device='cuda') for _ in range(n_sets)]
@@ -409,14 +421,23 @@ def main():
     def kernel_only(k):
         launch_rows(k, 0, ny_local)
 
+    if world > 1:
+        peer_strip = peer_halo.PeerStripResidual(grid, region[0], region[1], region[2], ny_local, ny_local, n_sets)
+        peer_launch = [peer_strip.bind(k, Ud[k], Vd[k], Fs[k]) for k in range(n_sets)]
+
+    def step_nccl(k):
+        # baseline: one NCCL group (both neighbours) issued from C on the launch stream, then the
+        # kernel; stream order makes the kernel see the halos
+        comm.halo_exchange(Xbuf[k].data_ptr() + 8 * row, row, ny_local, stream)
+        launch_rows(k, 0, ny_local)
+
     def step(k):
         if world == 1:
             launch_rows(k, 0, ny_local)
             return
-        # one NCCL group (both neighbours) issued from C on the launch stream, then the kernel;
-        # stream order makes the kernel see the halos
-        comm.halo_exchange(Xbuf[k].data_ptr() + 8 * row, row, ny_local, stream)
-        launch_rows(k, 0, ny_local)
+        # ONE launch: boundary tiles handshake with the neighbour strips and read their rows from
+        # peer memory while the interior tiles stream (ldc_residual_peer)
+        peer_launch[k](stream)
 
     def barrier():
         if world > 1:
@@ -432,8 +453,10 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
+    t_host = time.perf_counter()
     for k in range(steps):
         step(k % n_sets)
+    host_us = (time.perf_counter() - t_host) / steps * 1e6   # enqueue cost per step on this rank
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -452,6 +475,30 @@ def main():
         ms_total = float(t.item())
     ms_step = ms_total / steps
     value = N * world / (ms_step * 1e-3) / 1e6
+    nccl_ms = None
+    if world > 1:
+        if peer_strip.status():
+            raise RuntimeError("peer halo handshake timed out")
+        # the same step with the NCCL halo exchange in front of the kernel, for comparison
+        for k in range(warm):
+            step_nccl(k % n_sets)
+        barrier()
+        ev0.record()
+        for k in range(steps):
+            step_nccl(k % n_sets)
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nccl_ms = float(t.item()) / steps
+        # both paths must give the same bits on every rank
+        step(0)
+        F_peer = Fs[0].clone()
+        Fs[0].zero_()
+        step_nccl(0)
+        same = torch.tensor([1.0 if torch.equal(F_peer, Fs[0]) else 0.0], dtype=torch.float64, device='cuda')
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        halo_identical = bool(same.item() == 1.0) and not peer_strip.status()
 
     # ---- kernel-only roofline (single launch stream, CUDA events, no halo exchange)
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -495,8 +542,9 @@ def main():
         "steps": steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "residual F(X) of a 1024x1024 Re=1000 cavity per GPU (SURVEY 8d synthetic "
-                               "inputs); N>1: row strips of a 1024x(1024*N) grid with a one-row NCCL halo "
-                               "exchange per evaluation",
+                               "inputs); N>1: row strips of a 1024x(1024*N) grid, the one-row halos read "
+                               "from the neighbour GPUs' memory inside the kernel (flag handshake, "
+                               "no collective)",
                    "grid_per_gpu": [NX, NY], "l2": "L2-cold: rotating %d buffer sets (%.0f MB) > 126 MB L2" % (
                        n_sets, n_sets * res_bytes / 1e6),
                    "kernel": "residual_march_kernel (flux form, bit-exact arithmetic)"},
@@ -513,6 +561,10 @@ def main():
         "gpu_launches": steps,
         "clocks": clocks,
     }
+    if nccl_ms is not None:
+        line["halo"] = {"fused_peer_ms_per_step": ms_step, "nccl_sendrecv_then_kernel_ms_per_step": nccl_ms,
+                        "kernel_only_ms": kern_ms, "bit_identical_to_nccl_path": halo_identical,
+                        "host_enqueue_us_per_step": round(host_us, 2)}
     if not args.no_cpu:
         v, cores, kind, sample, best = cpu_reference_residual()
         line["cpu_baseline"] = {"value": v, "unit": "Mcells/s", "cores": cores, "kind": kind, "sample": sample}

@@ -69,6 +69,32 @@ LDC_API int ldc_residual(const ldc_grid *g, const double *X_dev, const double *U
                  const double *V_old_dev, double *F_dev, double *norm2_dev, double *work_dev,
                  int32_t variant, void *stream);
 
+/* ---- residual of one row strip with the halo exchange fused into the kernel (the
+ * reference has no multi-rank path).  Instead of receiving ghost rows into the local buffer
+ * before the launch, the tiles that touch the strip's first / last owned row read the
+ * neighbour's boundary row directly from peer-mapped memory (NVLink loads) after a
+ * flag handshake inside the kernel, so the evaluation is ONE launch and the transfer overlaps
+ * the interior tiles.  Protocol, per evaluation number `epoch` (1, 2, 3, ... identical on all
+ * strips): a boundary tile (a) stores `epoch` with release/system scope into the neighbour's
+ * flag word -- "my rows of X are final" (true by stream order at kernel start) -- and (b) spins
+ * until its own flag word from that neighbour is >= epoch, then reads the neighbour's row with
+ * system-scope loads.  The caller must not overwrite X before the neighbours have finished the
+ * same epoch (any collective in between guarantees it; bench.py rotates buffers).  A wait that
+ * does not complete within a few seconds sets *status_dev = 1 and the kernel finishes anyway
+ * (results invalid) -- it never hangs the device.  batch must be 1. */
+typedef struct ldc_peer_halo {
+    const double *prev_row;        /* LAST owned row of strip r-1 (3*nx doubles), peer-mapped; NULL on the first strip */
+    const double *next_row;        /* FIRST owned row of strip r+1, peer-mapped; NULL on the last strip               */
+    unsigned long long *my_flags;  /* local device memory, [0] is written by strip r-1, [1] by strip r+1, start at 0 */
+    unsigned long long *prev_flag; /* peer address of strip r-1's my_flags[1] (NULL on the first strip)              */
+    unsigned long long *next_flag; /* peer address of strip r+1's my_flags[0] (NULL on the last strip)               */
+    unsigned long long epoch;      /* evaluation counter, strictly increasing, same on every strip                  */
+    int32_t *status_dev;           /* optional: set to 1 when a wait timed out                                       */
+} ldc_peer_halo;
+LDC_API int ldc_residual_peer(const ldc_grid *g, const ldc_peer_halo *peer, const double *X_dev,
+                      const double *U_old_dev, const double *V_old_dev, double *F_dev,
+                      double *norm2_dev, double *work_dev, void *stream);
+
 /* ---- packing: replaces _create_X / _recover_X (nonlinear_solver/_common.py:4-36) */
 LDC_API int ldc_pack_X(const ldc_grid *g, const double *U_dev, const double *V_dev, const double *P_dev,
                double *X_dev, void *stream);

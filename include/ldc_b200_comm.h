@@ -42,6 +42,13 @@ LDC_API int ldc_comm_halo_exchange(ldc_comm *c, double *first_owned_row_dev, int
 LDC_API int ldc_comm_allreduce(ldc_comm *c, double *buf_dev, int64_t count, int32_t op, void *stream);
 /* in-place all-gather of `count` doubles per rank (rank r's piece at buf_dev + r*count) */
 LDC_API int ldc_comm_allgather(ldc_comm *c, double *buf_dev, int64_t count, void *stream);
+/* Peer-mapped device memory for ldc_residual_peer (include/ldc_b200.h): a COLLECTIVE call, every
+ * rank passing the same `bytes`.  *local is a zero-filled cudaMalloc region of this rank; *prev /
+ * *next are the regions of ranks r-1 / r+1 mapped into this process (CUDA IPC over NVLink; NULL
+ * where there is no neighbour), so offset k in *prev is offset k of rank r-1's *local.
+ * ldc_comm_peer_free is collective too. */
+LDC_API int ldc_comm_peer_alloc(ldc_comm *c, int64_t bytes, void **local, void **prev, void **next);
+LDC_API int ldc_comm_peer_free(ldc_comm *c, void *local);
 /* function table to hand to ldc_solver_set_comm */
 LDC_API const ldc_comm_ops *ldc_comm_get_ops(ldc_comm *c);
 

@@ -19,6 +19,8 @@ COMM_SYMBOLS = {
     'ldc_comm_halo_exchange': (ctypes.c_int, [_vp, _vp, _i64, _i64, _vp]),
     'ldc_comm_allreduce': (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
     'ldc_comm_allgather': (ctypes.c_int, [_vp, _vp, _i64, _vp]),
+    'ldc_comm_peer_alloc': (ctypes.c_int, [_vp, _i64, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    'ldc_comm_peer_free': (ctypes.c_int, [_vp, _vp]),
     'ldc_comm_get_ops': (_vp, [_vp]),
 }
 _lib = None
@@ -92,6 +94,17 @@ class Comm(object):
                                            1 if op == 'max' else 0,
                                            stream if stream is not None else _native.current_stream()),
               'ldc_comm_allreduce')
+
+    def peer_alloc(self, nbytes):
+        """collective: (local, prev, next) device addresses of a zero-filled region of ``nbytes`` on
+        this rank and of the neighbour ranks' regions mapped into this process (0 where none)"""
+        loc, prv, nxt = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        check(self._lib.ldc_comm_peer_alloc(self._handle, int(nbytes), ctypes.byref(loc), ctypes.byref(prv),
+                                            ctypes.byref(nxt)), 'ldc_comm_peer_alloc')
+        return loc.value or 0, prv.value or 0, nxt.value or 0
+
+    def peer_free(self, local):
+        check(self._lib.ldc_comm_peer_free(self._handle, ctypes.c_void_p(local)), 'ldc_comm_peer_free')
 
     def close(self):
         if self._handle is not None:

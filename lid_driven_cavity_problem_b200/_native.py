@@ -47,6 +47,13 @@ class LdcNewtonReport(ctypes.Structure):
                 ('xnorm', ctypes.c_double), ('ynorm', ctypes.c_double)]
 
 
+class LdcPeerHalo(ctypes.Structure):
+    _fields_ = [('prev_row', ctypes.c_void_p), ('next_row', ctypes.c_void_p),
+                ('my_flags', ctypes.c_void_p), ('prev_flag', ctypes.c_void_p),
+                ('next_flag', ctypes.c_void_p), ('epoch', ctypes.c_uint64),
+                ('status_dev', ctypes.c_void_p)]
+
+
 PC_NONE, PC_VANKA, PC_MG_VANKA = 0, 1, 2
 
 # every symbol include/ldc_b200.h declares: name -> (restype, argtypes)
@@ -59,6 +66,7 @@ SYMBOLS = {
     'ldc_device_info': (ctypes.c_int, [c_int32_p, c_int32_p, c_int32_p, ctypes.POINTER(_i64)]),
     'ldc_residual_work_doubles': (_i64, [_grid_p]),
     'ldc_residual': (ctypes.c_int, [_grid_p, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    'ldc_residual_peer': (ctypes.c_int, [_grid_p, ctypes.POINTER(LdcPeerHalo), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'ldc_pack_X': (ctypes.c_int, [_grid_p, _vp, _vp, _vp, _vp, _vp]),
     'ldc_unpack_X': (ctypes.c_int, [_grid_p, _vp, _vp, _vp, _vp, _vp]),
     'ldc_mask_nnz': (_i64, [_i32, _i32, _i32]),

@@ -9,12 +9,19 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/ldc_b200_comm.h"
+
+struct PeerRegion {
+    void *local, *prev, *next;
+};
 
 struct ldc_comm {
     ncclComm_t comm;
     int rank, nranks;
     ldc_comm_ops ops;
+    std::vector<PeerRegion> regions;
 };
 
 static thread_local char g_comm_error[512] = "";
@@ -24,6 +31,12 @@ static int comm_fail(const char *what, const char *detail)
     snprintf(g_comm_error, sizeof(g_comm_error), "%s: %s", what, detail);
     return LDC_ERR_CUDA;
 }
+
+#define LDC_RT(call)                                                         \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess) return comm_fail(#call, cudaGetErrorString(e__)); \
+    } while (0)
 
 #define LDC_NCCL(call)                                                       \
     do {                                                                     \
@@ -131,4 +144,65 @@ extern "C" int ldc_comm_allgather(ldc_comm *c, double *buf, int64_t count, void 
     LDC_NCCL(ncclAllGather(buf + (size_t)c->rank * count, buf, (size_t)count, ncclDouble, c->comm,
                            (cudaStream_t)stream));
     return LDC_OK;
+}
+
+// ---- peer-mapped regions: the memory behind ldc_residual_peer (include/ldc_b200.h).  Every rank
+// allocates the same number of bytes; CUDA IPC handles travel through one NCCL all-gather and the
+// two neighbours' regions are mapped into this process, so kernels can load the neighbour's
+// boundary rows and store its flag words directly over NVLink.
+extern "C" int ldc_comm_peer_alloc(ldc_comm *c, int64_t bytes, void **local_out, void **prev_out,
+                                   void **next_out)
+{
+    if (!c || bytes <= 0 || !local_out || !prev_out || !next_out)
+        return comm_fail("ldc_comm_peer_alloc", "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    PeerRegion r{nullptr, nullptr, nullptr};
+    LDC_RT(cudaMalloc(&r.local, (size_t)bytes));
+    LDC_RT(cudaMemset(r.local, 0, (size_t)bytes));
+    if (c->nranks > 1) {
+        cudaIpcMemHandle_t mine;
+        LDC_RT(cudaIpcGetMemHandle(&mine, r.local));
+        std::vector<cudaIpcMemHandle_t> all((size_t)c->nranks);
+        void *hbuf = nullptr;
+        LDC_RT(cudaMalloc(&hbuf, 64 * (size_t)c->nranks));
+        LDC_RT(cudaMemcpy((char *)hbuf + 64 * (size_t)c->rank, &mine, 64, cudaMemcpyHostToDevice));
+        LDC_NCCL(ncclAllGather((char *)hbuf + 64 * (size_t)c->rank, hbuf, 64, ncclChar, c->comm, 0));
+        LDC_RT(cudaStreamSynchronize(0));
+        LDC_RT(cudaMemcpy(all.data(), hbuf, 64 * (size_t)c->nranks, cudaMemcpyDeviceToHost));
+        LDC_RT(cudaFree(hbuf));
+        if (c->rank > 0)
+            LDC_RT(cudaIpcOpenMemHandle(&r.prev, all[c->rank - 1], cudaIpcMemLazyEnablePeerAccess));
+        if (c->rank < c->nranks - 1)
+            LDC_RT(cudaIpcOpenMemHandle(&r.next, all[c->rank + 1], cudaIpcMemLazyEnablePeerAccess));
+    }
+    c->regions.push_back(r);
+    *local_out = r.local;
+    *prev_out = r.prev;
+    *next_out = r.next;
+    return LDC_OK;
+}
+
+extern "C" int ldc_comm_peer_free(ldc_comm *c, void *local)
+{
+    if (!c || !local) return comm_fail("ldc_comm_peer_free", "bad arguments");
+    for (size_t k = 0; k < c->regions.size(); ++k) {
+        if (c->regions[k].local != local) continue;
+        PeerRegion r = c->regions[k];
+        c->regions.erase(c->regions.begin() + (long)k);
+        LDC_RT(cudaDeviceSynchronize());
+        if (r.prev) LDC_RT(cudaIpcCloseMemHandle(r.prev));
+        if (r.next) LDC_RT(cudaIpcCloseMemHandle(r.next));
+        if (c->nranks > 1) {
+            // nobody frees before every neighbour has dropped its mapping
+            double *tok = nullptr;
+            LDC_RT(cudaMalloc((void **)&tok, sizeof(double)));
+            LDC_RT(cudaMemset(tok, 0, sizeof(double)));
+            LDC_NCCL(ncclAllReduce(tok, tok, 1, ncclDouble, ncclSum, c->comm, 0));
+            LDC_RT(cudaStreamSynchronize(0));
+            LDC_RT(cudaFree(tok));
+        }
+        LDC_RT(cudaFree(r.local));
+        return LDC_OK;
+    }
+    return comm_fail("ldc_comm_peer_free", "unknown region");
 }

@@ -197,13 +197,19 @@ struct FluxOps {
 
 // One tile of rows for one block.  INTERIOR: no lane of the block touches a wall, the lid, a
 // dummy slot or a missing ghost row, so every mask below folds away at compile time.
-template <bool POW2, bool FAST, bool CDS, bool INTERIOR>
+// PEER (never together with INTERIOR): the ghost rows jl = -1 and jl = row_count are not in the
+// local buffer but the neighbour strips' boundary rows in peer-mapped memory (prev_row / next_row),
+// read with volatile loads so that no stale L1 line of an earlier epoch can be served.
+template <bool POW2, bool FAST, bool CDS, bool INTERIOR, bool PEER = false>
 __device__ __forceinline__ double march_tile(const ldc_grid &g, const Phys &p,
                                              const double *__restrict__ X,
                                              const double *__restrict__ U_old,
                                              const double *__restrict__ V_old,
-                                             double *__restrict__ F, int i, int lane, int jl0, int jl1)
+                                             double *__restrict__ F, int i, int lane, int jl0, int jl1,
+                                             const double *prev_row = nullptr,
+                                             const double *next_row = nullptr)
 {
+    static_assert(!(INTERIOR && PEER), "peer rows are handled by the general path");
     const FluxOps<POW2, FAST, CDS> fx(p);
     const int nx = g.nx, ny = g.ny;
     const bool writer = lane >= 1 && lane <= kMarchCols && (INTERIOR || i < nx);
@@ -220,7 +226,12 @@ __device__ __forceinline__ double march_tile(const ldc_grid &g, const Phys &p,
     const double *xcol = X + 3L * i;   // column i of local row 0 (may point before X for i = -1)
     auto load = [&](int jl, bool ok) {
         CellVals c;
-        if (INTERIOR || (ok && in_grid)) {
+        if (PEER && ok && in_grid && (jl < 0 || jl >= g.row_count)) {
+            const volatile double *q = (jl < 0 ? prev_row : next_row) + 3L * i;
+            c.P = q[0];
+            c.U = q[1];
+            c.V = q[2];
+        } else if (INTERIOR || (ok && in_grid)) {
             const double *q = xcol + row_stride * jl;
             c.P = __ldg(q);
             c.U = __ldg(q + 1);
@@ -376,6 +387,104 @@ residual_march_kernel(const ldc_grid g, const double *__restrict__ X,
             for (int w = 0; w < kMarchWarps; ++w) t += warp_sums[w];
             const long nblk = (long)gridDim.x * gridDim.y;
             partials[(long)inst * nblk + (long)blockIdx.y * gridDim.x + blockIdx.x] = t;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// variant 2 with the halo exchange fused in (ldc_residual_peer): same tiles and arithmetic; the
+// tiles that own the strip's first / last row handshake with the neighbour strip through flag
+// words and read its boundary row straight from peer memory over NVLink.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// bounded wait (~4 s): a lost neighbour must not hang the device
+__device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsigned long long epoch)
+{
+    for (long it = 0; it < (1L << 24); ++it) {
+        if (ld_acquire_sys(flag) >= epoch) return true;
+        __nanosleep(it < 64 ? 20 : 250);
+    }
+    return false;
+}
+
+template <bool POW2, bool FAST, bool CDS>
+__global__ void __launch_bounds__(kMarchWarps * 32, LDC_MARCH_MIN_BLOCKS)
+residual_march_peer_kernel(const ldc_grid g, const ldc_peer_halo peer, const double *__restrict__ X,
+                           const double *__restrict__ U_old, const double *__restrict__ V_old,
+                           double *__restrict__ F, double *__restrict__ partials, int rows_per_tile,
+                           int edge_rows)
+{
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const Phys p = make_phys(g, 0);
+
+    const int i_first = blockIdx.x * kMarchWarps * kMarchCols - 1;
+    const int i = i_first + warp * kMarchCols + lane;
+    // Row tiles: the rows next to a neighbour strip form their own SHORT tiles (edge_rows rows,
+    // blockIdx.y = 0 and 1 so they are scheduled first): they pay the handshake and the NVLink
+    // round trip, and being short they still finish before the full-height tiles in between.
+    int jl0, jl1;
+    {
+        const int e_prev = peer.prev_row ? edge_rows : 0, e_next = peer.next_row ? edge_rows : 0;
+        int by = blockIdx.y;
+        if (e_prev && by == 0) {
+            jl0 = 0; jl1 = e_prev;
+        } else if (e_next && by == (e_prev ? 1 : 0)) {
+            jl0 = g.row_count - e_next; jl1 = g.row_count;
+        } else {
+            by -= (e_prev ? 1 : 0) + (e_next ? 1 : 0);
+            jl0 = e_prev + by * rows_per_tile;
+            jl1 = min(jl0 + rows_per_tile, g.row_count - e_next);
+        }
+    }
+    const int i_last = i_first + (kMarchWarps - 1) * kMarchCols + 31;
+    const int jg0 = g.row_begin + jl0, jg1 = g.row_begin + jl1;
+    const bool needs_prev = jl0 == 0 && peer.prev_row != nullptr;
+    const bool needs_next = jl1 == g.row_count && peer.next_row != nullptr;
+    const bool interior = i_first >= 0 && i_last <= g.nx - 3 && jg0 >= 1 && jg1 <= g.ny - 2 &&
+                          !needs_prev && !needs_next;
+
+    double sq;
+    if (interior) {
+        sq = march_tile<POW2, FAST, CDS, true>(g, p, X, U_old, V_old, F, i, lane, jl0, jl1);
+    } else if (needs_prev || needs_next) {
+        if (threadIdx.x == 0) {
+            // X of this strip is final (stream order): tell the neighbour, then wait for its word
+            __threadfence_system();
+            if (needs_prev) st_release_sys(peer.prev_flag, peer.epoch);
+            if (needs_next) st_release_sys(peer.next_flag, peer.epoch);
+            bool ok = true;
+            if (needs_prev) ok = wait_flag(peer.my_flags + 0, peer.epoch) && ok;
+            if (needs_next) ok = wait_flag(peer.my_flags + 1, peer.epoch) && ok;
+            if (!ok && peer.status_dev) atomicExch(peer.status_dev, 1);
+        }
+        __syncthreads();
+        sq = march_tile<POW2, FAST, CDS, false, true>(g, p, X, U_old, V_old, F, i, lane, jl0, jl1,
+                                                      peer.prev_row, peer.next_row);
+    } else {
+        sq = march_tile<POW2, FAST, CDS, false>(g, p, X, U_old, V_old, F, i, lane, jl0, jl1);
+    }
+
+    if (partials) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        __shared__ double warp_sums[kMarchWarps];
+        if (lane == 0) warp_sums[warp] = sq;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < kMarchWarps; ++w) t += warp_sums[w];
+            partials[(long)blockIdx.y * gridDim.x + blockIdx.x] = t;
         }
     }
 }
@@ -692,6 +801,7 @@ sum_partials_kernel(const double *__restrict__ partials, long per_instance, doub
 struct MarchPlan {
     dim3 grid;
     int rows_per_tile;
+    int edge_rows = 0;
 };
 
 static MarchPlan plan_march(const ldc_grid &g)
@@ -720,6 +830,53 @@ static MarchPlan plan_march(const ldc_grid &g)
     pl.rows_per_tile = best_rows;
     pl.grid = dim3(col_blocks, (g.row_count + best_rows - 1) / best_rows, g.batch);
     return pl;
+}
+
+// ldc_residual_peer: short edge tiles next to the neighbour strips (see the kernel), the rows in
+// between tiled like plan_march but with the edge blocks counted, so that the whole grid still
+// fits the resident slots in whole waves.
+static MarchPlan plan_march_peer(const ldc_grid &g, bool has_prev, bool has_next)
+{
+    // the plan only depends on (nx, row_count, neighbours): keep the last one, the call sits on
+    // a path whose kernel runs for tens of microseconds
+    struct Key { int nx, rows, prev, next; };
+    static thread_local Key last_key{0, 0, 0, 0};
+    static thread_local MarchPlan last_plan;
+    if (last_key.nx == g.nx && last_key.rows == g.row_count && last_key.prev == (int)has_prev &&
+        last_key.next == (int)has_next)
+        return last_plan;
+    const int col_warps = (g.nx + kMarchCols - 1) / kMarchCols;
+    const int col_blocks = (col_warps + kMarchWarps - 1) / kMarchWarps;
+    const long slots = 4L * sm_count();
+    const int n_edges = (has_prev ? 1 : 0) + (has_next ? 1 : 0);
+    const char *env = getenv("LDC_PEER_EDGE_ROWS");
+    const int edge_candidates[3] = {4, 8, 2};
+    MarchPlan best_plan;
+    double best = -1.0;
+    for (int c = 0; c < 3; ++c) {
+        int edge = env ? atoi(env) : edge_candidates[c];
+        if (edge < 0 || n_edges == 0 || g.row_count < n_edges * edge + 8) edge = 0;   // thin strips: uniform tiles
+        const int mid = g.row_count - n_edges * edge;
+        const int extra = edge ? n_edges : 0;
+        const int lo = mid < 8 ? mid : 8;
+        for (int rows = lo; rows <= 64 && rows <= mid; ++rows) {
+            if (edge && 2 * edge > rows) continue;   // edge tiles must stay the short ones
+            const long blocks = (long)col_blocks * ((mid + rows - 1) / rows + extra);
+            const long waves = (blocks + slots - 1) / slots;
+            const double balance = (double)blocks / (double)(waves * slots);
+            const double score = balance * (double)rows / ((double)rows + 2.5);
+            if (score > best) {
+                best = score;
+                best_plan.rows_per_tile = rows;
+                best_plan.edge_rows = edge;
+                best_plan.grid = dim3(col_blocks, (mid + rows - 1) / rows + extra, 1);
+            }
+        }
+        if (env || edge == 0) break;
+    }
+    last_key = Key{g.nx, g.row_count, (int)has_prev, (int)has_next};
+    last_plan = best_plan;
+    return best_plan;
 }
 
 // rows per tile for the ring kernel: tall tiles amortise the pipeline fill (2 rows) and the halo
@@ -758,8 +915,11 @@ extern "C" int64_t ldc_residual_work_doubles(const ldc_grid *g)
     long a = (long)pl.grid.x * pl.grid.y;
     const long b = cell_blocks(*g);
     const long c = (long)pt.grid.x * pt.grid.y;
+    const MarchPlan pp = plan_march_peer(*g, true, true);
+    const long d = (long)pp.grid.x * pp.grid.y;
     if (b > a) a = b;
     if (c > a) a = c;
+    if (d > a) a = d;
     return a * g->batch;
 }
 
@@ -840,6 +1000,62 @@ extern "C" int ldc_residual(const ldc_grid *g, const double *X_dev, const double
     LDC_CHECK_LAUNCH();
     if (norm2_dev) {
         sum_partials_kernel<<<g->batch, 256, 0, s>>>(partials, per_instance, norm2_dev);
+        LDC_CHECK_LAUNCH();
+    }
+    return LDC_OK;
+}
+
+extern "C" int ldc_residual_peer(const ldc_grid *g, const ldc_peer_halo *peer, const double *X_dev,
+                                 const double *U_old_dev, const double *V_old_dev, double *F_dev,
+                                 double *norm2_dev, double *work_dev, void *stream)
+{
+    if (int rc = validate_grid(g, false)) return rc;
+    LDC_REQUIRE(peer, "ldc_residual_peer: null peer description");
+    LDC_REQUIRE(X_dev && U_old_dev && V_old_dev && F_dev, "ldc_residual_peer: null device pointer");
+    LDC_REQUIRE(X_dev != F_dev, "ldc_residual_peer: F must not alias X");
+    LDC_REQUIRE(!norm2_dev || work_dev, "ldc_residual_peer: norm2 requested without work buffer");
+    LDC_REQUIRE(g->batch == 1, "ldc_residual_peer: batch must be 1");
+    LDC_REQUIRE((g->row_begin > 0) == (peer->prev_row != nullptr) &&
+                    (g->row_begin + g->row_count < g->ny) == (peer->next_row != nullptr),
+                "ldc_residual_peer: prev_row/next_row must be set exactly where a neighbour strip exists");
+    LDC_REQUIRE((!peer->prev_row || peer->prev_flag) && (!peer->next_row || peer->next_flag) &&
+                    (peer->my_flags || (!peer->prev_row && !peer->next_row)),
+                "ldc_residual_peer: missing flag words");
+    LDC_REQUIRE(peer->epoch > 0, "ldc_residual_peer: epoch starts at 1");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool pow2 = is_pow2_double(g->dx) && is_pow2_double(g->dy);
+    const bool fast = pow2 && g->rho == 1.0 && g->mi == 1.0;
+    double *partials = norm2_dev ? work_dev : nullptr;
+    const MarchPlan pl = plan_march_peer(*g, peer->prev_row != nullptr, peer->next_row != nullptr);
+    const int edge_arg = pl.edge_rows;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = pl.grid;
+    cfg.blockDim = dim3(kMarchWarps * 32);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    static const bool no_pdl = getenv("LDC_NO_PDL") != nullptr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    const int rows_arg = pl.rows_per_tile;
+#define LDC_LAUNCH_PEER(P2, FA, CD)                                                                   \
+    LDC_CUDA(cudaLaunchKernelEx(&cfg, residual_march_peer_kernel<P2, FA, CD>, *g, *peer, X_dev,       \
+                                U_old_dev, V_old_dev, F_dev, partials, rows_arg, edge_arg))
+    if (g->use_cds) {
+        if (fast) LDC_LAUNCH_PEER(true, true, true);
+        else if (pow2) LDC_LAUNCH_PEER(true, false, true);
+        else LDC_LAUNCH_PEER(false, false, true);
+    } else {
+        if (fast) LDC_LAUNCH_PEER(true, true, false);
+        else if (pow2) LDC_LAUNCH_PEER(true, false, false);
+        else LDC_LAUNCH_PEER(false, false, false);
+    }
+#undef LDC_LAUNCH_PEER
+    LDC_CHECK_LAUNCH();
+    if (norm2_dev) {
+        sum_partials_kernel<<<1, 256, 0, s>>>(partials, (long)pl.grid.x * pl.grid.y, norm2_dev);
         LDC_CHECK_LAUNCH();
     }
     return LDC_OK;

@@ -67,3 +67,4 @@ def test_option_struct_layout_and_defaults():
     assert o.gmres_restart == 30 and o.pc_type == _native.PC_MG_VANKA
     assert o.pc_omega_u == 0.8 and o.pc_omega_p == 0.8      # last fields: a layout slip would garble them
     assert ctypes.sizeof(_native.LdcGrid) == 88 and ctypes.sizeof(_native.LdcNewtonReport) == 56
+    assert ctypes.sizeof(_native.LdcPeerHalo) == 56

@@ -133,6 +133,94 @@ def test_residual_row_strips(cuda):
         assert np.array_equal(out, F_ref), v
 
 
+@pytest.mark.parametrize("nx,ny,bounds", [(96, 70, [0, 17, 18, 40, 70]), (250, 128, [0, 64, 128]),
+                                          (1024, 512, [0, 128, 256, 384, 512])])
+def test_residual_peer_halo_strips_one_gpu(cuda, nx, ny, bounds):
+    """ldc_residual_peer: the strips read their neighbours' boundary rows from the neighbours'
+    regions after the in-kernel flag handshake.  Here all strips live on one GPU (one region and
+    one stream each, so the kernels overlap like ranks do); result bit-exact, twice in a row
+    (second epoch on changed X), status word clean."""
+    from oracle import ldc_oracle as orc
+    from lid_driven_cavity_problem_b200 import peer_halo
+    torch, native = cuda['torch'], cuda['native']
+    g, X = synthetic_case(nx, ny)
+    U_old = g.ns_x_mesh.phi_old.reshape(ny, nx - 1)
+    V_old = g.ns_y_mesh.phi_old.reshape(ny - 1, nx)
+    spans = list(zip(bounds[:-1], bounds[1:]))
+    rows_max = max(j1 - j0 for j0, j1 in spans)
+    nbytes = peer_halo.region_bytes(nx, rows_max, 1)
+    regions = [torch.zeros(nbytes // 8, dtype=torch.float64, device='cuda') for _ in spans]
+    strips, Us, Vs, Fs, streams = [], [], [], [], []
+    for r, (j0, j1) in enumerate(spans):
+        grid = native.grid_from_graph(g, row_begin=j0, row_count=j1 - j0)
+        prev = regions[r - 1].data_ptr() if r > 0 else 0
+        nxt = regions[r + 1].data_ptr() if r + 1 < len(spans) else 0
+        prev_rows = spans[r - 1][1] - spans[r - 1][0] if r > 0 else 0
+        strips.append(peer_halo.PeerStripResidual(grid, regions[r].data_ptr(), prev, nxt, prev_rows, rows_max))
+        Us.append(torch.from_numpy(U_old[j0:j1].copy().ravel()).cuda())
+        Vl = V_old[j0:min(j1, ny - 1)].copy().ravel()
+        Vs.append(torch.from_numpy(Vl if Vl.size else np.zeros(1)).cuda())
+        Fs.append(torch.full((3 * nx * (j1 - j0),), np.nan, dtype=torch.float64, device='cuda'))
+        streams.append(torch.cuda.Stream())
+    # all strips share one process here: a lazily loaded kernel (first use of the norm reduction)
+    # would make the host wait for strip 0's kernel, which waits for strip 1's launch -> load it now
+    cuda['crf'].residual_function_device(torch.from_numpy(X).cuda(), g, variant=2,
+                                         norm2_out=torch.zeros(1, dtype=torch.float64, device='cuda'))
+    for epoch in range(2):
+        Xe = X * (1.0 + 0.25 * epoch)
+        F_ref = orc.residual_function(Xe, g)
+        for r, (j0, j1) in enumerate(spans):
+            strips[r].x_tensor(0).copy_(torch.from_numpy(Xe[3 * nx * j0:3 * nx * j1].copy()))
+        torch.cuda.synchronize()
+        n2 = [torch.zeros(1, dtype=torch.float64, device='cuda') for _ in spans]
+        work = [torch.zeros(int(native.lib().ldc_residual_work_doubles(s.grid)), dtype=torch.float64,
+                            device='cuda') for s in strips]
+        for r in range(len(spans)):
+            with torch.cuda.stream(streams[r]):
+                strips[r].residual(0, Us[r], Vs[r], Fs[r], norm2=n2[r], work=work[r])
+        torch.cuda.synchronize()
+        out = np.concatenate([F.cpu().numpy() for F in Fs])
+        assert not any(s.status() for s in strips)
+        assert np.array_equal(out, F_ref), epoch
+        total = sum(float(t.item()) for t in n2)
+        assert abs(total - float(np.dot(F_ref, F_ref))) <= 1e-12 * float(np.dot(F_ref, F_ref))
+
+
+def test_residual_peer_halo_times_out_instead_of_hanging(cuda):
+    """a strip whose neighbour never shows up finishes (status word set) instead of hanging"""
+    from lid_driven_cavity_problem_b200 import peer_halo
+    torch, native = cuda['torch'], cuda['native']
+    nx, ny = 64, 32
+    g, X = synthetic_case(nx, ny)
+    nbytes = peer_halo.region_bytes(nx, 16, 1)
+    mine = torch.zeros(nbytes // 8, dtype=torch.float64, device='cuda')
+    ghost_town = torch.zeros(nbytes // 8, dtype=torch.float64, device='cuda')
+    grid = native.grid_from_graph(g, row_begin=0, row_count=16)
+    strip = peer_halo.PeerStripResidual(grid, mine.data_ptr(), 0, ghost_town.data_ptr(), 0, 16)
+    strip.x_tensor(0).copy_(torch.from_numpy(X[:3 * nx * 16].copy()))
+    U = torch.from_numpy(g.ns_x_mesh.phi_old[:(nx - 1) * 16].copy()).cuda()
+    V = torch.from_numpy(g.ns_y_mesh.phi_old[:nx * 16].copy()).cuda()
+    F = torch.empty(3 * nx * 16, dtype=torch.float64, device='cuda')
+    strip.residual(0, U, V, F)
+    assert strip.status()          # timed out, reported, device still alive
+    assert torch.isfinite(F[:3 * nx * 8]).all()
+
+
+def test_residual_peer_rejects_inconsistent_neighbours(cuda):
+    from lid_driven_cavity_problem_b200 import peer_halo
+    torch, native = cuda['torch'], cuda['native']
+    g, X = synthetic_case(32, 32)
+    buf = torch.zeros(peer_halo.region_bytes(32, 16, 1) // 8, dtype=torch.float64, device='cuda')
+    grid = native.grid_from_graph(g, row_begin=8, row_count=16)
+    with pytest.raises(ValueError):
+        peer_halo.PeerStripResidual(grid, buf.data_ptr(), 0, buf.data_ptr(), 8, 16)
+    ph = native.LdcPeerHalo()
+    ph.epoch = 1
+    rc = native.lib().ldc_residual_peer(grid, ph, native.ptr(buf), native.ptr(buf), native.ptr(buf),
+                                        buf.data_ptr() + 8 * 4096, None, None, native.current_stream())
+    assert rc != 0 and b'neighbour' in native.lib().ldc_last_error()
+
+
 def test_mask_bit_exact(cuda, golden):
     from oracle import ldc_oracle as orc
     common = cuda['common']
