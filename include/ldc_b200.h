@@ -75,10 +75,12 @@ LDC_API int ldc_residual(const ldc_grid *g, const double *X_dev, const double *U
  * neighbour's boundary row directly from peer-mapped memory (NVLink loads) after a
  * flag handshake inside the kernel, so the evaluation is ONE launch and the transfer overlaps
  * the interior tiles.  Protocol, per evaluation number `epoch` (1, 2, 3, ... identical on all
- * strips): a boundary tile (a) stores `epoch` with release/system scope into the neighbour's
- * flag word -- "my rows of X are final" (true by stream order at kernel start) -- and (b) spins
- * until its own flag word from that neighbour is >= epoch, then reads the neighbour's row with
- * system-scope loads.  The caller must not overwrite X before the neighbours have finished the
+ * strips): a boundary tile (a) stores `epoch` (system scope) into the neighbour's flag word --
+ * "my rows of X are final", true by stream order at kernel start, and already visible to peers
+ * because earlier kernels wrote them -- and (b) spins until its own flag word from that
+ * neighbour is >= epoch, then reads the neighbour's row with L1-bypassing loads.  X must
+ * therefore be produced by kernels that completed before this launch (stream order), not by
+ * this kernel.  The caller must not overwrite X before the neighbours have finished the
  * same epoch (any collective in between guarantees it; bench.py rotates buffers).  A wait that
  * does not complete within a few seconds sets *status_dev = 1 and the kernel finishes anyway
  * (results invalid) -- it never hangs the device.  batch must be 1. */

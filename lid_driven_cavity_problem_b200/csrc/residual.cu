@@ -396,21 +396,25 @@ residual_march_kernel(const ldc_grid g, const double *__restrict__ X,
 // tiles that own the strip's first / last row handshake with the neighbour strip through flag
 // words and read its boundary row straight from peer memory over NVLink.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+// Flag words are plain system-scope (relaxed) accesses, no fences: the data they announce was
+// written by EARLIER kernels of the neighbour's stream, so it reached that GPU's L2 -- where peer
+// loads are served -- at the kernel boundary; a sys-scope release/acquire pair here would only
+// add two MEMBAR.SYS (several microseconds each while the other tiles stream at full bandwidth).
+__device__ __forceinline__ void st_flag_sys(unsigned long long *p, unsigned long long v)
 {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+__device__ __forceinline__ unsigned long long ld_flag_sys(const unsigned long long *p)
 {
     unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 // bounded wait (~4 s): a lost neighbour must not hang the device
 __device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsigned long long epoch)
 {
     for (long it = 0; it < (1L << 24); ++it) {
-        if (ld_acquire_sys(flag) >= epoch) return true;
+        if (ld_flag_sys(flag) >= epoch) return true;
         __nanosleep(it < 64 ? 20 : 250);
     }
     return false;
@@ -460,9 +464,8 @@ residual_march_peer_kernel(const ldc_grid g, const ldc_peer_halo peer, const dou
     } else if (needs_prev || needs_next) {
         if (threadIdx.x == 0) {
             // X of this strip is final (stream order): tell the neighbour, then wait for its word
-            __threadfence_system();
-            if (needs_prev) st_release_sys(peer.prev_flag, peer.epoch);
-            if (needs_next) st_release_sys(peer.next_flag, peer.epoch);
+            if (needs_prev) st_flag_sys(peer.prev_flag, peer.epoch);
+            if (needs_next) st_flag_sys(peer.next_flag, peer.epoch);
             bool ok = true;
             if (needs_prev) ok = wait_flag(peer.my_flags + 0, peer.epoch) && ok;
             if (needs_next) ok = wait_flag(peer.my_flags + 1, peer.epoch) && ok;

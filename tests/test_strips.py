@@ -37,6 +37,49 @@ def test_comm_library_exports_every_declared_symbol():
     assert set(_comm.COMM_SYMBOLS) == set(declared)
 
 
+
+def test_peer_halo_region_layout_and_handshake_addresses(monkeypatch):
+    """host logic of peer_halo.PeerStripResidual (no GPU): where a strip looks for its neighbours'
+    boundary rows and flag words inside their regions, and the epoch bookkeeping"""
+    import ctypes
+    from lid_driven_cavity_problem_b200 import _native, peer_halo
+    nx, rows_max, n_sets = 12, 10, 3
+    row_b = 8 * 3 * nx
+    set_b = row_b * (rows_max + 2)
+    assert peer_halo.region_bytes(nx, rows_max, n_sets) == peer_halo.HEADER_BYTES + n_sets * set_b
+    g = _native.LdcGrid()
+    g.nx, g.ny, g.row_begin, g.row_count, g.batch = nx, 27, 7, 10, 1
+    calls = []
+
+    class FakeLib(object):
+        @staticmethod
+        def ldc_residual_peer(grid, ph_ref, X, U, V, F, n2, work, stream):
+            ph = ph_ref._obj
+            calls.append((ph.prev_row, ph.next_row, ph.my_flags, ph.prev_flag, ph.next_flag, ph.epoch,
+                          ph.status_dev, X.value))
+            return 0
+    local, prev, nxt = 0x100000, 0x200000, 0x300000
+    monkeypatch.setattr(_native, 'lib', lambda: FakeLib)
+    strip = peer_halo.PeerStripResidual(g, local, prev, nxt, prev_rows=7, rows_max=rows_max, n_sets=n_sets)
+    launch = strip.bind(2, None, None, None)
+    launch(ctypes.c_void_p(0))
+    launch(ctypes.c_void_p(0))
+    off = peer_halo.HEADER_BYTES + 2 * set_b
+    p_row, n_row, flags, p_flag, n_flag, epoch, status, x = calls[-1]
+    assert p_row == prev + off + row_b * 7          # ghost slot + 7 owned rows -> its LAST owned row
+    assert n_row == nxt + off + row_b               # its FIRST owned row
+    assert (flags, p_flag, n_flag) == (local, prev + 8, nxt)
+    assert status == local + peer_halo.STATUS_OFFSET and x == local + off + row_b
+    assert [c[5] for c in calls] == [1, 2]          # one epoch per evaluation
+    # first / last strips have one neighbour only; a missing region is refused
+    g.row_begin, g.row_count = 0, 7
+    first = peer_halo.PeerStripResidual(g, local, 0, nxt, 0, rows_max, n_sets)
+    first.residual(0, None, None, None, ctypes.c_void_p(0))
+    assert calls[-1][0] is None and calls[-1][3] is None and calls[-1][1] == nxt + peer_halo.HEADER_BYTES + row_b
+    with pytest.raises(ValueError):
+        peer_halo.PeerStripResidual(g, local, 0, 0, 0, rows_max, n_sets)
+
+
 _WORKER = r'''
 import os, sys
 sys.path.insert(0, os.environ["LDC_REPO"])
