@@ -462,18 +462,31 @@ residual_march_peer_kernel(const ldc_grid g, const ldc_peer_halo peer, const dou
     if (interior) {
         sq = march_tile<POW2, FAST, CDS, true>(g, p, X, U_old, V_old, F, i, lane, jl0, jl1);
     } else if (needs_prev || needs_next) {
+        // X of this strip is final (stream order): tell the neighbour first
         if (threadIdx.x == 0) {
-            // X of this strip is final (stream order): tell the neighbour, then wait for its word
             if (needs_prev) st_flag_sys(peer.prev_flag, peer.epoch);
             if (needs_next) st_flag_sys(peer.next_flag, peer.epoch);
+        }
+        // ... then the rows of the tile that only need local rows, so that the neighbour's word
+        // has normally arrived by the time it is looked at and only the one row next to the
+        // neighbour sits behind the wait and the NVLink round trip
+        const int a0 = jl0 + (needs_prev ? 1 : 0), a1 = jl1 - (needs_next ? 1 : 0);
+        sq = 0.0;
+        if (a1 > a0) sq = march_tile<POW2, FAST, CDS, false>(g, p, X, U_old, V_old, F, i, lane, a0, a1);
+        if (threadIdx.x == 0) {
             bool ok = true;
             if (needs_prev) ok = wait_flag(peer.my_flags + 0, peer.epoch) && ok;
             if (needs_next) ok = wait_flag(peer.my_flags + 1, peer.epoch) && ok;
             if (!ok && peer.status_dev) atomicExch(peer.status_dev, 1);
         }
         __syncthreads();
-        sq = march_tile<POW2, FAST, CDS, false, true>(g, p, X, U_old, V_old, F, i, lane, jl0, jl1,
-                                                      peer.prev_row, peer.next_row);
+        // the row(s) next to the neighbour; a one-row tile with both neighbours is one call
+        if (needs_prev)
+            sq += march_tile<POW2, FAST, CDS, false, true>(g, p, X, U_old, V_old, F, i, lane, jl0, jl0 + 1,
+                                                           peer.prev_row, peer.next_row);
+        if (needs_next && !(needs_prev && jl1 - jl0 == 1))
+            sq += march_tile<POW2, FAST, CDS, false, true>(g, p, X, U_old, V_old, F, i, lane, jl1 - 1, jl1,
+                                                           peer.prev_row, peer.next_row);
     } else {
         sq = march_tile<POW2, FAST, CDS, false>(g, p, X, U_old, V_old, F, i, lane, jl0, jl1);
     }
