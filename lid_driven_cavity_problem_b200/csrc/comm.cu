@@ -35,7 +35,10 @@ static int comm_fail(const char *what, const char *detail)
 #define LDC_RT(call)                                                         \
     do {                                                                     \
         cudaError_t e__ = (call);                                            \
-        if (e__ != cudaSuccess) return comm_fail(#call, cudaGetErrorString(e__)); \
+        if (e__ != cudaSuccess) {                                            \
+            (void)cudaGetLastError(); /* do not leave it for the next launch check */ \
+            return comm_fail(#call, cudaGetErrorString(e__));                \
+        }                                                                    \
     } while (0)
 
 #define LDC_NCCL(call)                                                       \
