@@ -102,6 +102,13 @@ extern "C" int ldc_comm_create(const void *id_bytes, int32_t nranks, int32_t ran
 extern "C" void ldc_comm_destroy(ldc_comm *c)
 {
     if (!c) return;
+    // regions the caller did not hand back: unmap the neighbours', free ours (no collective here)
+    for (const PeerRegion &r : c->regions) {
+        if (r.prev) cudaIpcCloseMemHandle(r.prev);
+        if (r.next) cudaIpcCloseMemHandle(r.next);
+        cudaFree(r.local);
+    }
+    c->regions.clear();
     ncclCommDestroy(c->comm);
     delete c;
 }
