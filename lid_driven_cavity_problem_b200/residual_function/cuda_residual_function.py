@@ -16,6 +16,9 @@ Reads exactly what the reference's native residual reads from ``graph``
 Unlike the C++ module, which reinterprets whatever buffer it is given as float64
 (SURVEY App. G), X is validated and converted to C-contiguous float64.
 """
+import os
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 
 from lid_driven_cavity_problem_b200 import _native
@@ -46,12 +49,35 @@ def _as_f64(name, host, n):
     return arr
 
 
+_pool = None
+
+
+def _copy_threads():
+    ranks_here = int(os.environ.get('LOCAL_WORLD_SIZE', '1') or 1)
+    return max(1, min(8, (os.cpu_count() or 1) // max(ranks_here, 1)))
+
+
+def _parallel_copy(dst, src):
+    """dst[:] = src for flat contiguous float64 numpy arrays, split over a small thread pool (numpy
+    drops the GIL inside copyto).  Deliberately not torch's copy_: its threading follows
+    OMP_NUM_THREADS, which torchrun sets to 1 for every worker."""
+    global _pool
+    n, nt = dst.size, _copy_threads()
+    if nt == 1 or n < (1 << 18):
+        np.copyto(dst, src)
+        return
+    if _pool is None:
+        _pool = ThreadPoolExecutor(max_workers=8, thread_name_prefix='ldc-stage')
+    step = -(-n // nt)
+    list(_pool.map(lambda a: np.copyto(dst[a:a + step], src[a:a + step]), range(0, n, step)))
+
+
 def _to_device(name, host, n, torch):
     """host array -> device tensor: multi-threaded copy into a cached pinned buffer, then an
     asynchronous DMA on the current stream (the next array is staged while this one travels)"""
     arr = _as_f64(name, host, n)
     pin = _pinned(name, n, torch)
-    pin.copy_(torch.from_numpy(arr))
+    _parallel_copy(pin.numpy(), arr)
     return pin.to('cuda', non_blocking=True)
 
 
@@ -95,5 +121,5 @@ def residual_function(X, graph):
     out.copy_(F_dev, non_blocking=True)
     result = np.empty(n, dtype=np.float64)      # freshly allocated, like the reference backends
     torch.cuda.current_stream().synchronize()
-    torch.from_numpy(result).copy_(out)         # multi-threaded host copy out of the pinned buffer
+    _parallel_copy(result, out.numpy())         # multi-threaded host copy out of the pinned buffer
     return result
