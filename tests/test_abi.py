@@ -68,3 +68,22 @@ def test_option_struct_layout_and_defaults():
     assert o.pc_omega_u == 0.8 and o.pc_omega_p == 0.8      # last fields: a layout slip would garble them
     assert ctypes.sizeof(_native.LdcGrid) == 88 and ctypes.sizeof(_native.LdcNewtonReport) == 56
     assert ctypes.sizeof(_native.LdcPeerHalo) == 56
+
+
+def test_host_staging_copy_is_exact_on_both_paths():
+    """the plug-in's host staging copy (torch threads, or the own pool when torchrun pinned torch to
+    one thread) moves every element, including a ragged tail"""
+    import numpy as np
+    import torch
+    from lid_driven_cavity_problem_b200.residual_function import cuda_residual_function as crf
+    before = torch.get_num_threads()
+    try:
+        for nt in (max(before, 2), 1):
+            torch.set_num_threads(nt)
+            for n in (1, 1000, (1 << 18) + 5, 3 * 700 * 700 + 1):
+                src = np.random.default_rng(n).random(n)
+                dst = np.full(n, -1.0)
+                crf._parallel_copy(dst, src, torch)
+                assert np.array_equal(dst, src), (nt, n)
+    finally:
+        torch.set_num_threads(before)
