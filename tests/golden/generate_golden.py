@@ -143,6 +143,31 @@ def main():
     gU = np.loadtxt(os.path.join(REFERENCE, 'experiments', 'ghia_ghia_shin_results', 'U.txt'))
     gV = np.loadtxt(os.path.join(REFERENCE, 'experiments', 'ghia_ghia_shin_results', 'V.txt'))
     np.savez(os.path.join(HERE, 'ghia_reference_tables.npz'), U=gU, V=gV)
+
+    # ---- 6. central differencing: only the reference's numba backend honours graph.use_cds
+    #         (numba_residual_function.py:128-137,202-211,247); with use_cds=False it must equal
+    #         the C++ residual, with use_cds=True it is the golden vector of the CDS switch
+    from lid_driven_cavity_problem.residual_function import numba_residual_function
+    cds = {}
+    cds_cases = [(3, 2, 10.0, 0.01, 1.0, 1.0, 1.0, 1.0), (7, 5, 400.0, 0.02, 1.0, 2.0, 1.3, 0.7),
+                 (33, 20, 1000.0, 0.005, 2.0, 1.0, 0.9, 1.1), (64, 48, 3200.0, 0.01, 1.0, 1.0, 1.0, 1.0)]
+    for k, (nx, ny, bc, dt, sx, sy, rho, mi) in enumerate(cds_cases):
+        g = Graph(sx, sy, nx, ny, dt, rho, mi, bc)
+        U, V, P = synthetic_state(nx, ny, bc, 2000 + nx)
+        g.ns_x_mesh.phi_old = 0.9 * U
+        g.ns_y_mesh.phi_old = 0.9 * V
+        X = _create_X(U, V, P, g)
+        g.use_cds = False
+        F_uds = np.asarray(numba_residual_function.residual_function(X, g), dtype=np.float64)
+        assert np.array_equal(F_uds, np.asarray(cpp_residual_function.residual_function(X, g)))
+        g.use_cds = True
+        F_cds = np.asarray(numba_residual_function.residual_function(X, g), dtype=np.float64)
+        assert not np.array_equal(F_cds, F_uds)
+        cds['X_%d' % k], cds['F_cds_%d' % k], cds['F_uds_%d' % k] = X, F_cds, F_uds
+        cds['U_old_%d' % k], cds['V_old_%d' % k] = 0.9 * U, 0.9 * V
+        cds['params_%d' % k] = np.array([sx, sy, nx, ny, dt, rho, mi, bc])
+    cds['count'] = np.array(len(cds_cases))
+    np.savez_compressed(os.path.join(HERE, 'residual_cds_cases.npz'), **cds)
     print('golden fixtures written to', HERE)
 
 

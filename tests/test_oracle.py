@@ -79,6 +79,21 @@ def test_against_compiled_reference():
     assert not np.array_equal(orc.residual_function(X, g), np.asarray(ref.residual_function(X, g)))
 
 
+def test_central_differencing_against_reference_numba_backend(golden):
+    """graph.use_cds: golden vectors from the reference's numba backend, the only one that honours
+    the switch (numba_residual_function.py:128-137,202-211,247); bit-exact on and off"""
+    d = golden('residual_cds_cases.npz')
+    for k in range(int(d['count'])):
+        g = make_graph(d['params_%d' % k])
+        g.ns_x_mesh.phi_old = d['U_old_%d' % k]
+        g.ns_y_mesh.phi_old = d['V_old_%d' % k]
+        g.use_cds = False
+        assert np.array_equal(orc.residual_function(d['X_%d' % k], g), d['F_uds_%d' % k]), k
+        g.use_cds = True
+        assert np.array_equal(orc.residual_function(d['X_%d' % k], g), d['F_cds_%d' % k]), k
+        assert np.array_equal(orc.residual_function(d['X_%d' % k], g, nthreads=0), d['F_cds_%d' % k]), k
+
+
 def test_fd_jacobian_colouring_equals_column_by_column():
     """coloured 'ds' FD + zeroed wrap entries == one residual per column."""
     for nx, ny in [(9, 8), (7, 7), (13, 9), (4, 3)]:
