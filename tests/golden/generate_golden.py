@@ -42,6 +42,25 @@ def _import_reference():
     assert lid_driven_cavity_problem.__file__.startswith(REFERENCE)
 
 
+# scripted-solver scenarios for the time-stepper traces (also imported by tests/test_time_stepper.py)
+STEPPER_SCENARIOS = {
+    'steady': dict(dt=1e-2, final_time=None, decay=0.1, diverge_on_calls=(), always_diverge=False,
+                   minimum_dt=1e-6, adaptative_dt=True),
+    'steady_with_failures': dict(dt=1e-2, final_time=None, decay=0.2, diverge_on_calls=(1, 2, 5, 9),
+                                 always_diverge=False, minimum_dt=1e-6, adaptative_dt=True),
+    'steady_fixed_dt': dict(dt=1e-2, final_time=None, decay=0.1, diverge_on_calls=(), always_diverge=False,
+                            minimum_dt=1e-6, adaptative_dt=False),
+    'fixed_time': dict(dt=0.04, final_time=0.1, decay=0.5, diverge_on_calls=(), always_diverge=False,
+                       minimum_dt=1e-6, adaptative_dt=True),
+    'fixed_time_with_failure': dict(dt=0.03, final_time=0.1, decay=0.5, diverge_on_calls=(2,),
+                                    always_diverge=False, minimum_dt=1e-6, adaptative_dt=True),
+    'fixed_time_exact_multiple': dict(dt=0.025, final_time=0.1, decay=0.5, diverge_on_calls=(),
+                                      always_diverge=False, minimum_dt=1e-6, adaptative_dt=False),
+    'give_up': dict(dt=4e-6, final_time=None, decay=0.5, diverge_on_calls=(), always_diverge=True,
+                    minimum_dt=1e-6, adaptative_dt=True),
+}
+
+
 def synthetic_state(nx, ny, bc, seed):
     """SURVEY 8(d) synthetic inputs: mixed signs, nothing cancels."""
     rng = np.random.default_rng(seed)
@@ -168,6 +187,37 @@ def main():
         cds['params_%d' % k] = np.array([sx, sy, nx, ny, dt, rho, mi, bc])
     cds['count'] = np.array(len(cds_cases))
     np.savez_compressed(os.path.join(HERE, 'residual_cds_cases.npz'), **cds)
+
+    # ---- 7. traces of the reference pseudo-time driver (time_stepper.py:9-56) under scripted
+    #         solvers: which dt every solver call saw, the dt left on the caller's graph and on
+    #         the returned graph, the final U.  tests/test_time_stepper.py replays them.
+    import copy
+    from lid_driven_cavity_problem.nonlinear_solver.exceptions import SolverDivergedException
+    traces = {}
+    for name, sc in STEPPER_SCENARIOS.items():
+        calls = []
+
+        def solver(graph, sc=sc, calls=calls):
+            calls.append(graph.dt)
+            if len(calls) in sc['diverge_on_calls'] or sc['always_diverge']:
+                raise SolverDivergedException()
+            new = copy.deepcopy(graph)
+            new.ns_x_mesh.phi_old = np.array(graph.ns_x_mesh.phi)
+            new.ns_x_mesh.phi = sc['decay'] * np.array(graph.ns_x_mesh.phi)
+            return new
+        g = Graph(1.0, 1.0, 4, 4, sc['dt'], 1.0, 1.0, 10.0)
+        raised = 0
+        try:
+            out = run_simulation(g, sc['final_time'], solver, minimum_dt=sc['minimum_dt'],
+                                 adaptative_dt=sc['adaptative_dt'])
+        except RuntimeError:
+            raised, out = 1, g
+        traces[name + '_calls'] = np.array(calls)
+        traces[name + '_caller_dt'] = np.array(g.dt)
+        traces[name + '_out_dt'] = np.array(out.dt)
+        traces[name + '_out_U'] = np.array(out.ns_x_mesh.phi, dtype=np.float64)
+        traces[name + '_raised'] = np.array(raised)
+    np.savez(os.path.join(HERE, 'stepper_traces.npz'), **traces)
     print('golden fixtures written to', HERE)
 
 

@@ -89,3 +89,45 @@ def test_solver_builder_names_on_cpu():
     assert np.array_equal(out.ns_x_mesh.phi_old, g.ns_x_mesh.phi)
     F = orc.residual_function(orc.create_X(out.ns_x_mesh.phi, out.ns_y_mesh.phi, out.pressure_mesh.phi, out), out)
     assert np.abs(F).max() < 1e-6
+
+
+def _scenarios():
+    import importlib.util
+    import os
+    from conftest import GOLDEN
+    spec = importlib.util.spec_from_file_location('generate_golden', os.path.join(GOLDEN, 'generate_golden.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)        # module level only defines helpers; nothing of the reference is touched
+    return mod.STEPPER_SCENARIOS
+
+
+@pytest.mark.parametrize("name", ['steady', 'steady_with_failures', 'steady_fixed_dt', 'fixed_time',
+                                  'fixed_time_with_failure', 'fixed_time_exact_multiple', 'give_up'])
+def test_replays_the_reference_driver_traces(name, golden):
+    """tests/golden/stepper_traces.npz: the REFERENCE's run_simulation (time_stepper.py:9-56) under
+    scripted solvers -- every dt a solver call saw, the dt left on the caller's and on the returned
+    graph, the final U.  This driver must reproduce them exactly."""
+    sc = _scenarios()[name]
+    d = golden('stepper_traces.npz')
+    calls = []
+
+    def solver(graph):
+        calls.append(graph.dt)
+        if len(calls) in sc['diverge_on_calls'] or sc['always_diverge']:
+            raise SolverDivergedException()
+        new = copy.deepcopy(graph)
+        new.ns_x_mesh.phi_old = np.array(graph.ns_x_mesh.phi)
+        new.ns_x_mesh.phi = sc['decay'] * np.array(graph.ns_x_mesh.phi)
+        return new
+    g = make_graph([1.0, 1.0, 4, 4, sc['dt'], 1.0, 1.0, 10.0])
+    raised = 0
+    try:
+        out = run_simulation(g, sc['final_time'], solver, minimum_dt=sc['minimum_dt'],
+                             adaptative_dt=sc['adaptative_dt'])
+    except RuntimeError:
+        raised, out = 1, g
+    assert raised == int(d[name + '_raised'])
+    assert np.array_equal(np.array(calls), d[name + '_calls'])          # exact, not approximate
+    assert g.dt == float(d[name + '_caller_dt'])
+    assert out.dt == float(d[name + '_out_dt'])
+    assert np.array_equal(np.asarray(out.ns_x_mesh.phi, dtype=np.float64), d[name + '_out_U'])
