@@ -120,3 +120,41 @@ def test_ensemble_matches_individual_solves():
         out = run_simulation(g, None, solve, max_steps=summ[b]['steps'])
         assert np.abs(out.ns_x_mesh.phi - U[b]).max() <= 1e-9 * bc, (b, np.abs(out.ns_x_mesh.phi - U[b]).max())
         assert np.abs(out.ns_y_mesh.phi - V[b]).max() <= 1e-9 * bc
+
+
+@pytest.mark.parametrize("names,final_time", [
+    (['steady', 'steady_with_failures', 'give_up'], None),
+    (['fixed_time', 'fixed_time_with_failure'], 0.1)])
+def test_ensemble_stepper_replays_the_reference_driver_traces(names, final_time, golden):
+    """the per-cavity rules of EnsembleTimeStepper against tests/golden/stepper_traces.npz (the
+    REFERENCE's run_simulation under scripted solvers): cavities with different scripts advance in
+    one batch and each one must see exactly the dt sequence the reference driver produced"""
+    import importlib.util
+    from conftest import GOLDEN
+    from lid_driven_cavity_problem_b200.ensemble import EnsembleTimeStepper, FAILED
+    spec = importlib.util.spec_from_file_location('generate_golden', os.path.join(GOLDEN, 'generate_golden.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    scs = [mod.STEPPER_SCENARIOS[n] for n in names]
+    d = golden('stepper_traces.npz')
+    ts = EnsembleTimeStepper([sc['dt'] for sc in scs], [10.0] * len(scs), final_time=final_time)
+    calls = [[] for _ in scs]
+    U = np.ones(len(scs))                      # Graph default initial_U = 1.0 (staggered_grid.py:36)
+    for _ in range(100):
+        act = ts.active()
+        if not act.any():
+            break
+        dt = ts.begin_step()
+        reasons, du = np.full(len(scs), 3), np.zeros(len(scs))
+        for b in np.nonzero(act)[0]:
+            calls[b].append(dt[b])
+            if len(calls[b]) in scs[b]['diverge_on_calls'] or scs[b]['always_diverge']:
+                reasons[b] = -3
+            else:
+                du[b] = abs(scs[b]['decay'] * U[b] - U[b])
+                U[b] *= scs[b]['decay']
+        ts.end_step(reasons, du)
+    for b, n in enumerate(names):
+        assert np.array_equal(np.array(calls[b]), d[n + '_calls']), n
+        assert ts.dt[b] == float(d[n + '_out_dt']), n
+        assert (ts.status[b] == FAILED) == bool(d[n + '_raised']), n
