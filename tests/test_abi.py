@@ -87,3 +87,43 @@ def test_host_staging_copy_is_exact_on_both_paths():
                 assert np.array_equal(dst, src), (nt, n)
     finally:
         torch.set_num_threads(before)
+
+
+def test_argument_validation_happens_before_any_device_work():
+    """invalid calls are refused with LDC_ERR_INVALID and a message before CUDA is touched, so this
+    runs without a device; and with no device a valid call fails loudly instead of computing on the host"""
+    import ctypes
+    import numpy as np
+    import torch
+    from lid_driven_cavity_problem_b200 import _native
+    lib = _native.load_library()
+    g = _native.LdcGrid()
+    g.nx, g.ny, g.row_begin, g.row_count, g.batch = 8, 8, 0, 8, 1
+    g.dt, g.dx, g.dy, g.rho, g.mi, g.bc = 1e-2, 1 / 8, 1 / 8, 1.0, 1.0, 10.0
+    X, F = np.zeros(3 * 64), np.zeros(3 * 64)
+    px, pf = X.ctypes.data_as(ctypes.c_void_p), F.ctypes.data_as(ctypes.c_void_p)
+
+    def refused(rc, text):
+        return rc == -1 and text in lib.ldc_last_error()
+    assert refused(lib.ldc_residual(g, None, px, px, pf, None, None, 0, None), b'null device pointer')
+    assert refused(lib.ldc_residual(g, px, px, px, px, None, None, 0, None), b'must not alias')
+    assert refused(lib.ldc_residual(g, px, px, px, pf, None, None, 7, None), b'unknown variant')
+    assert refused(lib.ldc_residual(g, px, px, px, pf, pf, None, 0, None), b'without work buffer')
+    g.nx = 2
+    assert refused(lib.ldc_residual(g, px, px, px, pf, None, None, 0, None), b'too small')
+    g.nx, g.row_count = 8, 9
+    assert refused(lib.ldc_residual(g, px, px, px, pf, None, None, 0, None), b'outside grid')
+    g.row_count = 8
+    ph = _native.LdcPeerHalo()
+    assert refused(lib.ldc_residual_peer(g, ph, px, px, px, pf, None, None, None), b'epoch starts at 1')
+    ph.epoch = 1
+    ph.next_row = px          # a full grid has no neighbour strip
+    assert refused(lib.ldc_residual_peer(g, ph, px, px, px, pf, None, None, None), b'neighbour strip exists')
+    g.batch = 2
+    assert refused(lib.ldc_residual_peer(g, ph, px, px, px, pf, None, None, None), b'batch must be 1')
+    g.batch = 1
+    assert lib.ldc_residual_work_doubles(g) > 0
+    if not torch.cuda.is_available():
+        rc = lib.ldc_residual(g, px, px, px, pf, None, None, 0, None)
+        assert rc == -2 and b'CUDA error' in lib.ldc_last_error()
+        assert not F.any()                  # nothing was computed anywhere
