@@ -231,7 +231,7 @@ __device__ __forceinline__ double march_tile(const ldc_grid &g, const Phys &p,
             c.P = q[0];
             c.U = q[1];
             c.V = q[2];
-        } else if (INTERIOR || (ok && in_grid)) {
+        } else if (ok && (INTERIOR || in_grid)) {   // `ok` also bounds the prefetch of interior tiles
             const double *q = xcol + row_stride * jl;
             c.P = __ldg(q);
             c.U = __ldg(q + 1);
@@ -797,6 +797,8 @@ residual_tma_kernel(const ldc_grid g, const double *__restrict__ X,
     }
 }
 
+#include "residual_ring.cuh"
+
 // one block per instance: fixed-order sum of the per-block partials (deterministic)
 __global__ void __launch_bounds__(256)
 sum_partials_kernel(const double *__restrict__ partials, long per_instance, double *__restrict__ out)
@@ -917,6 +919,161 @@ static MarchPlan plan_tma(const ldc_grid &g)
     return pl;
 }
 
+// ---- variant 4 launch plan -------------------------------------------------------------------
+// {warps per block, ring stages per warp, resident blocks per SM aimed at, F through bulk stores}
+struct RingConfig { int warps, depth, min_blocks, bulk_store; };
+static constexpr RingConfig kRingConfigs[] = {{4, 3, 3, 0}, {4, 3, 3, 1}, {4, 4, 3, 0}, {4, 2, 3, 0},
+                                              {4, 3, 4, 0}, {2, 3, 6, 0}, {8, 3, 2, 0}};
+static constexpr int kNumRingConfigs = (int)(sizeof(kRingConfigs) / sizeof(kRingConfigs[0]));
+
+typedef void (*ring_kernel_t)(const ldc_grid, const RingPhys, const RingArgs, const double *, const double *,
+                              const double *, double *, double *);
+
+// the tuning configurations (LDC_RING_CFG) exist for the flavour the headline benchmark runs
+// (power-of-two spacing, rho = mi = 1, upwind); everything else uses configuration 0
+template <bool P2, bool FA, bool CD, bool NO>
+static ring_kernel_t ring_kernel_for(int cfg)
+{
+    if constexpr (FA && !CD && !NO) {
+        switch (cfg) {
+            case 1: return residual_ring_kernel<P2, FA, CD, NO, true, 4, 3, 3>;
+            case 2: return residual_ring_kernel<P2, FA, CD, NO, false, 4, 4, 3>;
+            case 3: return residual_ring_kernel<P2, FA, CD, NO, false, 4, 2, 3>;
+            case 4: return residual_ring_kernel<P2, FA, CD, NO, false, 4, 3, 4>;
+            case 5: return residual_ring_kernel<P2, FA, CD, NO, false, 2, 3, 6>;
+            case 6: return residual_ring_kernel<P2, FA, CD, NO, false, 8, 3, 2>;
+            default: break;
+        }
+    }
+    return residual_ring_kernel<P2, FA, CD, NO, false, 4, 3, 3>;
+}
+
+static int ring_env_int(const char *name, int dflt)
+{
+    const char *e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
+// tuning knobs are read once per process (environment lookups do not belong on a 15 us path)
+struct RingTuning { int cfg, rows, pdl; };
+static const RingTuning &ring_tuning()
+{
+    static const RingTuning t = [] {
+        RingTuning r;
+        r.cfg = ring_env_int("LDC_RING_CFG", 0);
+        if (r.cfg < 0 || r.cfg >= kNumRingConfigs) r.cfg = 0;
+        r.rows = ring_env_int("LDC_RING_ROWS", 0);
+        r.pdl = getenv("LDC_NO_PDL") == nullptr;
+        return r;
+    }();
+    return t;
+}
+
+struct RingLaunch {
+    ring_kernel_t fn = nullptr;
+    RingConfig cfg{};
+    int blocks_per_sm = 0;
+    size_t smem = 0;
+};
+
+// kernel flavour (pow2 / fast, cds, norm) -> function, dynamic shared memory opted in, occupancy
+// queried: once per flavour and process
+static int ring_launch_for(bool pow2, bool fast, bool cds, bool norm, RingLaunch **out)
+{
+    static RingLaunch cache[2][2][3];
+    const int fl = fast ? 2 : (pow2 ? 1 : 0);
+    RingLaunch &rl = cache[norm ? 1 : 0][cds ? 1 : 0][fl];
+    if (!rl.fn) {
+        int cfg = ring_tuning().cfg;
+        if (!(fast && !cds && !norm)) cfg = 0;
+        ring_kernel_t fn;
+#define LDC_RING_PICK(CD, NO)                                                                        \
+    (fast ? ring_kernel_for<true, true, CD, NO>(cfg)                                                 \
+          : pow2 ? ring_kernel_for<true, false, CD, NO>(cfg) : ring_kernel_for<false, false, CD, NO>(cfg))
+        if (cds) fn = norm ? LDC_RING_PICK(true, true) : LDC_RING_PICK(true, false);
+        else fn = norm ? LDC_RING_PICK(false, true) : LDC_RING_PICK(false, false);
+#undef LDC_RING_PICK
+        const RingConfig rc = kRingConfigs[cfg];
+        const size_t smem = (size_t)rc.warps * ring::warp_doubles(rc.depth, rc.bulk_store != 0) * sizeof(double);
+        LDC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        LDC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, rc.warps * 32, smem));
+        rl.cfg = rc;
+        rl.smem = smem;
+        rl.blocks_per_sm = nb > 0 ? nb : 1;
+        rl.fn = fn;
+    }
+    *out = &rl;
+    return LDC_OK;
+}
+
+static RingPhys ring_phys(const ldc_grid &g)
+{
+    // the same IEEE operations as make_phys / FluxOps on the device (no contraction on the host:
+    // every product below is a separate statement-level operation on doubles)
+    RingPhys p;
+    p.dx = g.dx;
+    p.dy = g.dy;
+    p.inv_dx = 1.0 / g.dx;
+    p.inv_dy = 1.0 / g.dy;
+    p.rho = g.rho;
+    p.mi = g.mi;
+    p.kx = p.inv_dx * g.dy;
+    p.ky = p.inv_dy * g.dx;
+    p.hx = 0.5 * g.dx;
+    p.hy = 0.5 * g.dy;
+    const double vol = g.dx * g.dy;
+    p.vol_dt = g.dt_dev ? 0.0 : vol / g.dt;
+    p.bc = g.bc;
+    return p;
+}
+
+static RingArgs plan_ring(const ldc_grid &g, int warps_per_sm)
+{
+    // the plan only depends on the grid shape: keep the last one
+    struct Key { int nx, rows, batch, wps; };
+    static thread_local Key last_key{0, 0, 0, 0};
+    static thread_local RingArgs last;
+    if (last_key.nx == g.nx && last_key.rows == g.row_count && last_key.batch == g.batch &&
+        last_key.wps == warps_per_sm)
+        return last;
+    RingArgs ra;
+    int n_strips = (g.nx + ring::kCols - 1) / ring::kCols;
+    ra.cols = ((g.nx + n_strips - 1) / n_strips + 1) & ~1;      // even share, <= 62
+    ra.n_strips = (g.nx + ra.cols - 1) / ra.cols;
+    // Rows per tile: a tile also streams its two halo rows (L2 hits, the neighbour tiles load them
+    // too), so tall tiles are cheaper, but the warps should fill the resident slots in whole waves.
+    const long slots = (long)warps_per_sm * sm_count();
+    int best_rows = g.row_count < 4 ? g.row_count : 4;
+    if (ring_tuning().rows > 0) {
+        best_rows = ring_tuning().rows < g.row_count ? ring_tuning().rows : g.row_count;
+    } else {
+        double best = -1.0;
+        for (int rows = best_rows; rows <= 128 && rows <= g.row_count; ++rows) {
+            const long items = (long)ra.n_strips * ((g.row_count + rows - 1) / rows) * g.batch;
+            const long waves = (items + slots - 1) / slots;
+            const double balance = (double)items / (double)(waves * slots);
+            const double score = balance * (double)rows / ((double)rows + 2.0);
+            if (score > best) { best = score; best_rows = rows; }
+        }
+    }
+    ra.rows = best_rows;
+    ra.n_row_tiles = (g.row_count + best_rows - 1) / best_rows;
+    ra.per_instance = (long)ra.n_strips * ra.n_row_tiles;
+    ra.total = ra.per_instance * g.batch;
+    ra.u_total = instance_strides(g).u * g.batch;
+    last_key = Key{g.nx, g.row_count, g.batch, warps_per_sm};
+    last = ra;
+    return ra;
+}
+
+static bool ring_eligible(const ldc_grid &g, const double *X, const double *U_old, const double *V_old,
+                          const double *F)
+{
+    return g.nx % 2 == 0 && g.nx >= 4 &&
+           ((((uintptr_t)X) | ((uintptr_t)U_old) | ((uintptr_t)V_old) | ((uintptr_t)F)) & 15) == 0;
+}
+
 static long cell_blocks(const ldc_grid &g) { return ((long)g.nx * g.row_count + 255) / 256; }
 
 }  // namespace ldc
@@ -933,9 +1090,15 @@ extern "C" int64_t ldc_residual_work_doubles(const ldc_grid *g)
     const long c = (long)pt.grid.x * pt.grid.y;
     const MarchPlan pp = plan_march_peer(*g, true, true);
     const long d = (long)pp.grid.x * pp.grid.y;
+    // variant 4 keeps one partial per warp-sized work item; its tiles are never shorter than
+    // min(4, row_count) rows unless LDC_RING_ROWS says so
+    const int min_rows = ring_tuning().rows > 0 ? ring_tuning().rows : 4;
+    const long strips = (g->nx + ring::kCols - 1) / ring::kCols + 1;
+    const long e = strips * ((g->row_count + min_rows - 1) / min_rows);
     if (b > a) a = b;
     if (c > a) a = c;
     if (d > a) a = d;
+    if (e > a) a = e;
     return a * g->batch;
 }
 
@@ -947,15 +1110,35 @@ extern "C" int ldc_residual(const ldc_grid *g, const double *X_dev, const double
     LDC_REQUIRE(X_dev && U_old_dev && V_old_dev && F_dev, "ldc_residual: null device pointer");
     LDC_REQUIRE(X_dev != F_dev, "ldc_residual: F must not alias X");
     LDC_REQUIRE(!norm2_dev || work_dev, "ldc_residual: norm2 requested without work buffer");
-    LDC_REQUIRE(variant >= 0 && variant <= 3, "ldc_residual: unknown variant %d", variant);
+    LDC_REQUIRE(variant >= 0 && variant <= 4, "ldc_residual: unknown variant %d", variant);
     cudaStream_t s = (cudaStream_t)stream;
     const bool pow2 = is_pow2_double(g->dx) && is_pow2_double(g->dy);
     double *partials = norm2_dev ? work_dev : nullptr;
     long per_instance;
     const bool tma_ok = (g->nx % 2 == 0) && (((uintptr_t)X_dev & 15) == 0) && g->row_count >= 2;
-    if (variant == 0) variant = 2;   // measured on B200: 2 beats 3 at every size (profiles/r1_sweep_c*)
+    if (variant == 0) variant = 4;
+    if (variant == 4 && !ring_eligible(*g, X_dev, U_old_dev, V_old_dev, F_dev)) variant = 2;
     if (variant == 3 && !tma_ok) variant = 2;
-    if (variant == 3) {
+    if (variant == 4) {
+        const bool fast = pow2 && g->rho == 1.0 && g->mi == 1.0;
+        RingLaunch *rl = nullptr;
+        if (int rc = ring_launch_for(pow2, fast, g->use_cds != 0, partials != nullptr, &rl)) return rc;
+        const RingArgs ra = plan_ring(*g, rl->blocks_per_sm * rl->cfg.warps);
+        const RingPhys rp = ring_phys(*g);
+        per_instance = ra.per_instance;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)((ra.total + rl->cfg.warps - 1) / rl->cfg.warps));
+        cfg.blockDim = dim3(rl->cfg.warps * 32);
+        cfg.dynamicSmemBytes = rl->smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = ring_tuning().pdl ? 1 : 0;
+        LDC_CUDA(cudaLaunchKernelEx(&cfg, rl->fn, *g, rp, ra, X_dev, U_old_dev, V_old_dev, F_dev, partials));
+    } else if (variant == 3) {
         const MarchPlan pl = plan_tma(*g);
         per_instance = (long)pl.grid.x * pl.grid.y;
         const bool fast = pow2 && g->rho == 1.0 && g->mi == 1.0;
