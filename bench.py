@@ -426,12 +426,26 @@ def main():
         if rc != 0:
             _native.check(rc, 'ldc_residual')
 
+    def bind_plain(k):
+        """ldc_residual of buffer set k with every argument converted once (the kernel runs for
+        ~13 us; rebuilding ctypes structures per call would make the loop host-bound)"""
+        args = (ctypes.byref(grid), ctypes.c_void_p(Xbuf[k].data_ptr() + 8 * row), _native.ptr(Ud[k]),
+                _native.ptr(Vd[k]), _native.ptr(Fs[k]), None, None, 0, stream)
+        fn = lib.ldc_residual
+
+        def launch():
+            rc = fn(*args)
+            if rc != 0:
+                _native.check(rc, 'ldc_residual')
+        return launch
+    plain_launch = [bind_plain(k) for k in range(n_sets)]
+
     def kernel_only(k):
-        launch_rows(k, 0, ny_local)
+        plain_launch[k]()
 
     if region is not None:
         peer_strip = peer_halo.PeerStripResidual(grid, region[0], region[1], region[2], ny_local, ny_local, n_sets)
-        peer_launch = [peer_strip.bind(k, Ud[k], Vd[k], Fs[k]) for k in range(n_sets)]
+        peer_launch = [peer_strip.bind_overlapped(k, Ud[k], Vd[k], Fs[k], lag=4) for k in range(n_sets)]
 
     def step_nccl(k):
         # baseline: one NCCL group (both neighbours) issued from C on the launch stream, then the
@@ -441,13 +455,17 @@ def main():
 
     def step(k):
         if world == 1:
-            launch_rows(k, 0, ny_local)
+            plain_launch[k]()
             return
         if peer_strip is None:
             step_nccl(k)
             return
-        # ONE launch: boundary tiles handshake with the neighbour strips and read their rows from
-        # peer memory while the interior tiles stream (ldc_residual_peer)
+        # Two launches, no collective: the halo push (this strip's boundary rows -> the neighbours'
+        # ghost rows + flag words, NVLink stores) on a high-priority side stream, overlapped with
+        # the residual kernel, whose boundary tiles wait for the neighbours' words and read the
+        # ghost rows locally.  One library call (ldc_residual_peer_step); flow control of the
+        # static-input loop: push(i) waits for this rank's kernel of step i-4, which keeps every
+        # push less than 8 evaluations ahead of the slowest neighbour (9 buffers in rotation).
         peer_launch[k](stream)
 
     def barrier():

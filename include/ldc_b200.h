@@ -61,41 +61,68 @@ LDC_API int ldc_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_mi
  * the five sibling backends.  F_dev is fully overwritten (dummy rows F=X).  When
  * norm2_dev != NULL, *norm2_dev receives sum(F^2) per instance ([batch] doubles), computed by a
  * deterministic two-stage reduction (work_dev must then hold ldc_residual_work_doubles()).
- * variant: 0 = auto, 1 = cell-per-thread reference kernel, 2 = flux-form column-marching kernel,
- *          3 = flux form with TMA-staged rows (needs even nx and 16-byte aligned X, else falls back to 2).
+ * variant: 0 = auto (4 when eligible, else 2), 1 = cell-per-thread reference kernel,
+ *          2 = flux-form column-marching kernel with register prefetch,
+ *          3 = flux form, rows staged per block through a TMA ring (even nx, 16-byte aligned X; else 2),
+ *          4 = flux form, one bulk-copy ring per warp, two cells per lane with 128-bit accesses
+ *              (even nx and 16-byte aligned X, U_old, V_old, F; else 2).
  */
 LDC_API int64_t ldc_residual_work_doubles(const ldc_grid *g);
 LDC_API int ldc_residual(const ldc_grid *g, const double *X_dev, const double *U_old_dev,
                  const double *V_old_dev, double *F_dev, double *norm2_dev, double *work_dev,
                  int32_t variant, void *stream);
 
-/* ---- residual of one row strip with the halo exchange fused into the kernel (the
- * reference has no multi-rank path).  Instead of receiving ghost rows into the local buffer
- * before the launch, the tiles that touch the strip's first / last owned row read the
- * neighbour's boundary row directly from peer-mapped memory (NVLink loads) after a
- * flag handshake inside the kernel, so the evaluation is ONE launch and the transfer overlaps
- * the interior tiles.  Protocol, per evaluation number `epoch` (1, 2, 3, ... identical on all
- * strips): a boundary tile (a) stores `epoch` (system scope) into the neighbour's flag word --
- * "my rows of X are final", true by stream order at kernel start, and already visible to peers
- * because earlier kernels wrote them -- and (b) spins until its own flag word from that
- * neighbour is >= epoch, then reads the neighbour's row with L1-bypassing loads.  X must
- * therefore be produced by kernels that completed before this launch (stream order), not by
- * this kernel.  The caller must not overwrite X before the neighbours have finished the
- * same epoch (any collective in between guarantees it; bench.py rotates buffers).  A wait that
- * does not complete within a few seconds sets *status_dev = 1 and the kernel finishes anyway
- * (results invalid) -- it never hangs the device.  batch must be 1. */
+/* ---- residual of one row strip per GPU without a collective (the reference has no
+ * multi-rank path).  Buffers use the strip layout above: [ghost row | row_count owned rows | ghost
+ * row], and every strip's buffer is mapped into its neighbours' address space (CUDA IPC / peer
+ * access, e.g. ldc_comm_peer_alloc).  One evaluation number `epoch` (1, 2, 3, ... identical on all
+ * strips) is two launches:
+ *   ldc_residual_peer_push   copies the strip's first / last owned row of X into the neighbours'
+ *                            ghost rows (NVLink stores) and then stores `epoch` (release, system
+ *                            scope) into the neighbours' flag words.  Small kernel; meant for a
+ *                            side stream so that it overlaps the residual kernel.  X must be final
+ *                            on that stream (the caller orders it after X's producer).
+ *   ldc_residual_peer        the residual kernel of ldc_residual; the tiles next to a neighbour
+ *                            strip wait (acquire, bounded) until their own flag word shows `epoch`
+ *                            and then read the ghost row from LOCAL memory.  It performs no remote
+ *                            access: a kernel that stores to peer memory pays a system-scope flush
+ *                            of ~2.6 us at its end (measured on B200), the push kernel takes that
+ *                            cost off the critical path.
+ * Because epoch k's ghost rows overwrite those of the last evaluation on the same buffer, a
+ * buffer must not be pushed into while the neighbour still evaluates an older epoch on it: rotate
+ * at least two X buffers and order push(k) after the own residual(k-1) (which cannot finish
+ * before the neighbours pushed k-1, i.e. before they finished k-2), or separate evaluations by
+ * any collective.  A wait that does not complete within a few seconds sets *status_dev = 1 and
+ * the kernel finishes anyway (results invalid) -- it never hangs the device.  batch must be 1. */
 typedef struct ldc_peer_halo {
-    const double *prev_row;        /* LAST owned row of strip r-1 (3*nx doubles), peer-mapped; NULL on the first strip */
-    const double *next_row;        /* FIRST owned row of strip r+1, peer-mapped; NULL on the last strip               */
+    double *prev_ghost;            /* in strip r-1's buffer (peer-mapped): the ghost row ABOVE its last owned row; NULL on the first strip */
+    double *next_ghost;            /* in strip r+1's buffer (peer-mapped): the ghost row BELOW its first owned row; NULL on the last strip  */
     unsigned long long *my_flags;  /* local device memory, [0] is written by strip r-1, [1] by strip r+1, start at 0 */
     unsigned long long *prev_flag; /* peer address of strip r-1's my_flags[1] (NULL on the first strip)              */
     unsigned long long *next_flag; /* peer address of strip r+1's my_flags[0] (NULL on the last strip)               */
     unsigned long long epoch;      /* evaluation counter, strictly increasing, same on every strip                  */
     int32_t *status_dev;           /* optional: set to 1 when a wait timed out                                       */
 } ldc_peer_halo;
+LDC_API int ldc_residual_peer_push(const ldc_grid *g, const ldc_peer_halo *peer, const double *X_dev,
+                           void *stream);
 LDC_API int ldc_residual_peer(const ldc_grid *g, const ldc_peer_halo *peer, const double *X_dev,
                       const double *U_old_dev, const double *V_old_dev, double *F_dev,
                       double *norm2_dev, double *work_dev, void *stream);
+/* Both launches of one evaluation in one call, overlapped: the push goes to a high-priority side
+ * stream owned by the context, the residual kernel to `stream`.  For loops over rotating X buffers
+ * whose contents are final before the loop starts (bench.py): the side stream is NOT ordered after
+ * work queued on `stream`, except that push(i) waits for this strip's residual kernel of
+ * evaluation i-lag.  That kernel needed the neighbours' push(i-lag), which waited for their
+ * kernels of evaluation i-2*lag, so a ghost row is never overwritten while a neighbour still
+ * reads it as long as more than 2*lag X buffers rotate; the event is `lag` evaluations old, so it
+ * never holds a push up in steady state.  A caller whose X is produced on `stream` between
+ * evaluations uses the two calls above with its own event instead. */
+typedef struct ldc_peer_ctx ldc_peer_ctx;
+LDC_API int ldc_peer_ctx_create(int32_t lag, ldc_peer_ctx **out);
+LDC_API void ldc_peer_ctx_destroy(ldc_peer_ctx *ctx);
+LDC_API int ldc_residual_peer_step(ldc_peer_ctx *ctx, const ldc_grid *g, const ldc_peer_halo *peer,
+                           const double *X_dev, const double *U_old_dev, const double *V_old_dev,
+                           double *F_dev, double *norm2_dev, double *work_dev, void *stream);
 
 /* ---- packing: replaces _create_X / _recover_X (nonlinear_solver/_common.py:4-36) */
 LDC_API int ldc_pack_X(const ldc_grid *g, const double *U_dev, const double *V_dev, const double *P_dev,

@@ -48,7 +48,7 @@ class LdcNewtonReport(ctypes.Structure):
 
 
 class LdcPeerHalo(ctypes.Structure):
-    _fields_ = [('prev_row', ctypes.c_void_p), ('next_row', ctypes.c_void_p),
+    _fields_ = [('prev_ghost', ctypes.c_void_p), ('next_ghost', ctypes.c_void_p),
                 ('my_flags', ctypes.c_void_p), ('prev_flag', ctypes.c_void_p),
                 ('next_flag', ctypes.c_void_p), ('epoch', ctypes.c_uint64),
                 ('status_dev', ctypes.c_void_p)]
@@ -66,7 +66,11 @@ SYMBOLS = {
     'ldc_device_info': (ctypes.c_int, [c_int32_p, c_int32_p, c_int32_p, ctypes.POINTER(_i64)]),
     'ldc_residual_work_doubles': (_i64, [_grid_p]),
     'ldc_residual': (ctypes.c_int, [_grid_p, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    'ldc_residual_peer_push': (ctypes.c_int, [_grid_p, ctypes.POINTER(LdcPeerHalo), _vp, _vp]),
     'ldc_residual_peer': (ctypes.c_int, [_grid_p, ctypes.POINTER(LdcPeerHalo), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'ldc_peer_ctx_create': (ctypes.c_int, [_i32, ctypes.POINTER(_vp)]),
+    'ldc_peer_ctx_destroy': (None, [_vp]),
+    'ldc_residual_peer_step': (ctypes.c_int, [_vp, _grid_p, ctypes.POINTER(LdcPeerHalo), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'ldc_pack_X': (ctypes.c_int, [_grid_p, _vp, _vp, _vp, _vp, _vp]),
     'ldc_unpack_X': (ctypes.c_int, [_grid_p, _vp, _vp, _vp, _vp, _vp]),
     'ldc_mask_nnz': (_i64, [_i32, _i32, _i32]),

@@ -392,22 +392,15 @@ residual_march_kernel(const ldc_grid g, const double *__restrict__ X,
 }
 
 // ---------------------------------------------------------------------------------------------
-// variant 2 with the halo exchange fused in (ldc_residual_peer): same tiles and arithmetic; the
-// tiles that own the strip's first / last row handshake with the neighbour strip through flag
-// words and read its boundary row straight from peer memory over NVLink.
+// variant 2 for one row strip per GPU (ldc_residual_peer when variant 4 is not eligible, i.e. odd
+// nx): same tiles and arithmetic; the ghost rows next to a neighbour strip arrive in the local
+// buffer through the neighbour's push kernel (halo_push_kernel below), the tiles that need them
+// wait for the neighbour's flag word first.
 // ---------------------------------------------------------------------------------------------
-// Flag words are plain system-scope (relaxed) accesses, no fences: the data they announce was
-// written by EARLIER kernels of the neighbour's stream, so it reached that GPU's L2 -- where peer
-// loads are served -- at the kernel boundary; a sys-scope release/acquire pair here would only
-// add two MEMBAR.SYS (several microseconds each while the other tiles stream at full bandwidth).
-__device__ __forceinline__ void st_flag_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 __device__ __forceinline__ unsigned long long ld_flag_sys(const unsigned long long *p)
 {
     unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 // bounded wait (~4 s): a lost neighbour must not hang the device
@@ -431,6 +424,9 @@ residual_march_peer_kernel(const ldc_grid g, const ldc_peer_halo peer, const dou
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const Phys p = make_phys(g, 0);
+    const bool has_prev = g.row_begin > 0, has_next = g.row_begin + g.row_count < g.ny;
+    // the ghost rows sit in the local buffer next to the owned rows (strip layout)
+    const double *prev_row = X - 3L * g.nx, *next_row = X + 3L * g.nx * g.row_count;
 
     const int i_first = blockIdx.x * kMarchWarps * kMarchCols - 1;
     const int i = i_first + warp * kMarchCols + lane;
@@ -439,7 +435,7 @@ residual_march_peer_kernel(const ldc_grid g, const ldc_peer_halo peer, const dou
     // round trip, and being short they still finish before the full-height tiles in between.
     int jl0, jl1;
     {
-        const int e_prev = peer.prev_row ? edge_rows : 0, e_next = peer.next_row ? edge_rows : 0;
+        const int e_prev = has_prev ? edge_rows : 0, e_next = has_next ? edge_rows : 0;
         int by = blockIdx.y;
         if (e_prev && by == 0) {
             jl0 = 0; jl1 = e_prev;
@@ -453,8 +449,8 @@ residual_march_peer_kernel(const ldc_grid g, const ldc_peer_halo peer, const dou
     }
     const int i_last = i_first + (kMarchWarps - 1) * kMarchCols + 31;
     const int jg0 = g.row_begin + jl0, jg1 = g.row_begin + jl1;
-    const bool needs_prev = jl0 == 0 && peer.prev_row != nullptr;
-    const bool needs_next = jl1 == g.row_count && peer.next_row != nullptr;
+    const bool needs_prev = jl0 == 0 && has_prev;
+    const bool needs_next = jl1 == g.row_count && has_next;
     const bool interior = i_first >= 0 && i_last <= g.nx - 3 && jg0 >= 1 && jg1 <= g.ny - 2 &&
                           !needs_prev && !needs_next;
 
@@ -462,14 +458,8 @@ residual_march_peer_kernel(const ldc_grid g, const ldc_peer_halo peer, const dou
     if (interior) {
         sq = march_tile<POW2, FAST, CDS, true>(g, p, X, U_old, V_old, F, i, lane, jl0, jl1);
     } else if (needs_prev || needs_next) {
-        // X of this strip is final (stream order): tell the neighbour first
-        if (threadIdx.x == 0) {
-            if (needs_prev) st_flag_sys(peer.prev_flag, peer.epoch);
-            if (needs_next) st_flag_sys(peer.next_flag, peer.epoch);
-        }
-        // ... then the rows of the tile that only need local rows, so that the neighbour's word
-        // has normally arrived by the time it is looked at and only the one row next to the
-        // neighbour sits behind the wait and the NVLink round trip
+        // first the rows of the tile that only need owned rows, so that the neighbour's word has
+        // normally arrived by the time it is looked at
         const int a0 = jl0 + (needs_prev ? 1 : 0), a1 = jl1 - (needs_next ? 1 : 0);
         sq = 0.0;
         if (a1 > a0) sq = march_tile<POW2, FAST, CDS, false>(g, p, X, U_old, V_old, F, i, lane, a0, a1);
@@ -483,10 +473,10 @@ residual_march_peer_kernel(const ldc_grid g, const ldc_peer_halo peer, const dou
         // the row(s) next to the neighbour; a one-row tile with both neighbours is one call
         if (needs_prev)
             sq += march_tile<POW2, FAST, CDS, false, true>(g, p, X, U_old, V_old, F, i, lane, jl0, jl0 + 1,
-                                                           peer.prev_row, peer.next_row);
+                                                           prev_row, next_row);
         if (needs_next && !(needs_prev && jl1 - jl0 == 1))
             sq += march_tile<POW2, FAST, CDS, false, true>(g, p, X, U_old, V_old, F, i, lane, jl1 - 1, jl1,
-                                                           peer.prev_row, peer.next_row);
+                                                           prev_row, next_row);
     } else {
         sq = march_tile<POW2, FAST, CDS, false>(g, p, X, U_old, V_old, F, i, lane, jl0, jl1);
     }
@@ -867,7 +857,7 @@ static MarchPlan plan_march_peer(const ldc_grid &g, bool has_prev, bool has_next
     const int col_blocks = (col_warps + kMarchWarps - 1) / kMarchWarps;
     const long slots = 4L * sm_count();
     const int n_edges = (has_prev ? 1 : 0) + (has_next ? 1 : 0);
-    const char *env = getenv("LDC_PEER_EDGE_ROWS");
+    static const char *env = getenv("LDC_PEER_EDGE_ROWS");
     const int edge_candidates[3] = {4, 8, 2};
     MarchPlan best_plan;
     double best = -1.0;
@@ -920,32 +910,29 @@ static MarchPlan plan_tma(const ldc_grid &g)
 }
 
 // ---- variant 4 launch plan -------------------------------------------------------------------
-// {warps per block, ring stages per warp, resident blocks per SM aimed at, F through bulk stores}
-struct RingConfig { int warps, depth, min_blocks, bulk_store; };
-static constexpr RingConfig kRingConfigs[] = {{4, 3, 3, 0}, {4, 3, 3, 1}, {4, 4, 3, 0}, {4, 2, 3, 0},
-                                              {4, 3, 4, 0}, {2, 3, 6, 0}, {8, 3, 2, 0}};
+// {warps per block, ring stages per warp, register cap per thread}
+struct RingConfig { int warps, depth, max_regs; };
+static constexpr RingConfig kRingConfigs[] = {{4, 3, 168}, {4, 4, 168}, {4, 2, 168}, {2, 3, 168}};
 static constexpr int kNumRingConfigs = (int)(sizeof(kRingConfigs) / sizeof(kRingConfigs[0]));
 
-typedef void (*ring_kernel_t)(const ldc_grid, const RingPhys, const RingArgs, const double *, const double *,
-                              const double *, double *, double *);
+typedef void (*ring_kernel_t)(const ldc_grid, const RingPhys, const RingArgs, const RingGhost, const double *,
+                              const double *, const double *, double *, double *);
 
 // the tuning configurations (LDC_RING_CFG) exist for the flavour the headline benchmark runs
-// (power-of-two spacing, rho = mi = 1, upwind); everything else uses configuration 0
-template <bool P2, bool FA, bool CD, bool NO>
+// (power-of-two spacing, rho = mi = 1, upwind, no norm, no neighbours); everything else uses
+// configuration 0
+template <bool P2, bool FA, bool CD, bool NO, bool PE>
 static ring_kernel_t ring_kernel_for(int cfg)
 {
-    if constexpr (FA && !CD && !NO) {
+    if constexpr (FA && !CD && !NO && !PE) {
         switch (cfg) {
-            case 1: return residual_ring_kernel<P2, FA, CD, NO, true, 4, 3, 3>;
-            case 2: return residual_ring_kernel<P2, FA, CD, NO, false, 4, 4, 3>;
-            case 3: return residual_ring_kernel<P2, FA, CD, NO, false, 4, 2, 3>;
-            case 4: return residual_ring_kernel<P2, FA, CD, NO, false, 4, 3, 4>;
-            case 5: return residual_ring_kernel<P2, FA, CD, NO, false, 2, 3, 6>;
-            case 6: return residual_ring_kernel<P2, FA, CD, NO, false, 8, 3, 2>;
+            case 1: return residual_ring_kernel<P2, FA, CD, NO, PE, 4, 4, 168>;
+            case 2: return residual_ring_kernel<P2, FA, CD, NO, PE, 4, 2, 168>;
+            case 3: return residual_ring_kernel<P2, FA, CD, NO, PE, 2, 3, 168>;
             default: break;
         }
     }
-    return residual_ring_kernel<P2, FA, CD, NO, false, 4, 3, 3>;
+    return residual_ring_kernel<P2, FA, CD, NO, PE, 4, 3, 168>;
 }
 
 static int ring_env_int(const char *name, int dflt)
@@ -955,7 +942,7 @@ static int ring_env_int(const char *name, int dflt)
 }
 
 // tuning knobs are read once per process (environment lookups do not belong on a 15 us path)
-struct RingTuning { int cfg, rows, pdl; };
+struct RingTuning { int cfg, rows, pdl, debug, edge_rows; };
 static const RingTuning &ring_tuning()
 {
     static const RingTuning t = [] {
@@ -964,6 +951,8 @@ static const RingTuning &ring_tuning()
         if (r.cfg < 0 || r.cfg >= kNumRingConfigs) r.cfg = 0;
         r.rows = ring_env_int("LDC_RING_ROWS", 0);
         r.pdl = getenv("LDC_NO_PDL") == nullptr;
+        r.debug = ring_env_int("LDC_PEER_DEBUG", 0);
+        r.edge_rows = ring_env_int("LDC_PEER_EDGE_ROWS", -1);
         return r;
     }();
     return t;
@@ -976,25 +965,27 @@ struct RingLaunch {
     size_t smem = 0;
 };
 
-// kernel flavour (pow2 / fast, cds, norm) -> function, dynamic shared memory opted in, occupancy
-// queried: once per flavour and process
-static int ring_launch_for(bool pow2, bool fast, bool cds, bool norm, RingLaunch **out)
+// kernel flavour (pow2 / fast, cds, norm, peer) -> function, dynamic shared memory opted in,
+// occupancy queried: once per flavour and process
+static int ring_launch_for(bool pow2, bool fast, bool cds, bool norm, bool peer, RingLaunch **out)
 {
-    static RingLaunch cache[2][2][3];
+    static RingLaunch cache[2][2][2][3];
     const int fl = fast ? 2 : (pow2 ? 1 : 0);
-    RingLaunch &rl = cache[norm ? 1 : 0][cds ? 1 : 0][fl];
+    RingLaunch &rl = cache[peer ? 1 : 0][norm ? 1 : 0][cds ? 1 : 0][fl];
     if (!rl.fn) {
         int cfg = ring_tuning().cfg;
-        if (!(fast && !cds && !norm)) cfg = 0;
+        if (!(fast && !cds && !norm && !peer)) cfg = 0;
         ring_kernel_t fn;
-#define LDC_RING_PICK(CD, NO)                                                                        \
-    (fast ? ring_kernel_for<true, true, CD, NO>(cfg)                                                 \
-          : pow2 ? ring_kernel_for<true, false, CD, NO>(cfg) : ring_kernel_for<false, false, CD, NO>(cfg))
-        if (cds) fn = norm ? LDC_RING_PICK(true, true) : LDC_RING_PICK(true, false);
-        else fn = norm ? LDC_RING_PICK(false, true) : LDC_RING_PICK(false, false);
+#define LDC_RING_PICK(CD, NO, PE)                                                                        \
+    (fast ? ring_kernel_for<true, true, CD, NO, PE>(cfg)                                                 \
+          : pow2 ? ring_kernel_for<true, false, CD, NO, PE>(cfg) : ring_kernel_for<false, false, CD, NO, PE>(cfg))
+#define LDC_RING_PICK2(CD, NO) (peer ? LDC_RING_PICK(CD, NO, true) : LDC_RING_PICK(CD, NO, false))
+        if (cds) fn = norm ? LDC_RING_PICK2(true, true) : LDC_RING_PICK2(true, false);
+        else fn = norm ? LDC_RING_PICK2(false, true) : LDC_RING_PICK2(false, false);
+#undef LDC_RING_PICK2
 #undef LDC_RING_PICK
         const RingConfig rc = kRingConfigs[cfg];
-        const size_t smem = (size_t)rc.warps * ring::warp_doubles(rc.depth, rc.bulk_store != 0) * sizeof(double);
+        const size_t smem = (size_t)rc.warps * ring::warp_doubles(rc.depth, false) * sizeof(double);
         LDC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
         LDC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, rc.warps * 32, smem));
@@ -1002,6 +993,9 @@ static int ring_launch_for(bool pow2, bool fast, bool cds, bool norm, RingLaunch
         rl.smem = smem;
         rl.blocks_per_sm = nb > 0 ? nb : 1;
         rl.fn = fn;
+        if (getenv("LDC_RING_VERBOSE"))
+            fprintf(stderr, "[ldc] ring kernel pow2=%d fast=%d cds=%d norm=%d peer=%d: %d blocks of %d warps per SM, %zu B smem\n",
+                    (int)pow2, (int)fast, (int)cds, (int)norm, (int)peer, rl.blocks_per_sm, rc.warps, smem);
     }
     *out = &rl;
     return LDC_OK;
@@ -1028,6 +1022,14 @@ static RingPhys ring_phys(const ldc_grid &g)
     return p;
 }
 
+static void ring_strips(int nx, int *n_strips, int *cols)
+{
+    const int n = (nx + ring::kCols - 1) / ring::kCols;
+    *cols = ((nx + n - 1) / n + 1) & ~1;      // even share, <= 62
+    *n_strips = (nx + *cols - 1) / *cols;
+}
+
+// uniform row tiles over the rows of `g` (ldc_residual, and the rows between the edge tiles of a strip)
 static RingArgs plan_ring(const ldc_grid &g, int warps_per_sm)
 {
     // the plan only depends on the grid shape: keep the last one
@@ -1038,9 +1040,8 @@ static RingArgs plan_ring(const ldc_grid &g, int warps_per_sm)
         last_key.wps == warps_per_sm)
         return last;
     RingArgs ra;
-    int n_strips = (g.nx + ring::kCols - 1) / ring::kCols;
-    ra.cols = ((g.nx + n_strips - 1) / n_strips + 1) & ~1;      // even share, <= 62
-    ra.n_strips = (g.nx + ra.cols - 1) / ra.cols;
+    memset(&ra, 0, sizeof(ra));
+    ring_strips(g.nx, &ra.n_strips, &ra.cols);
     // Rows per tile: a tile also streams its two halo rows (L2 hits, the neighbour tiles load them
     // too), so tall tiles are cheaper, but the warps should fill the resident slots in whole waves.
     const long slots = (long)warps_per_sm * sm_count();
@@ -1062,6 +1063,9 @@ static RingArgs plan_ring(const ldc_grid &g, int warps_per_sm)
     ra.per_instance = (long)ra.n_strips * ra.n_row_tiles;
     ra.total = ra.per_instance * g.batch;
     ra.u_total = instance_strides(g).u * g.batch;
+    if (getenv("LDC_RING_VERBOSE"))
+        fprintf(stderr, "[ldc] ring plan %dx%d x%d: %d strips of %d columns, %d row tiles of %d rows, %ld warps on %ld slots\n",
+                g.nx, g.row_count, g.batch, ra.n_strips, ra.cols, ra.n_row_tiles, ra.rows, ra.total, slots);
     last_key = Key{g.nx, g.row_count, g.batch, warps_per_sm};
     last = ra;
     return ra;
@@ -1072,6 +1076,95 @@ static bool ring_eligible(const ldc_grid &g, const double *X, const double *U_ol
 {
     return g.nx % 2 == 0 && g.nx >= 4 &&
            ((((uintptr_t)X) | ((uintptr_t)U_old) | ((uintptr_t)V_old) | ((uintptr_t)F)) & 15) == 0;
+}
+
+// rows of the short tiles next to a neighbour strip (0: the strip is too thin for separate edge tiles)
+static int ring_edge_rows(const ldc_grid &g, int n_edges)
+{
+    int edge = ring_tuning().edge_rows >= 0 ? ring_tuning().edge_rows : 4;
+    if (n_edges == 0 || g.row_count < n_edges * edge + 4) edge = 0;
+    return edge;
+}
+
+// ldc_residual_peer (one launch): short tiles next to the neighbour strips first (they wait for
+// the pushes and must still finish with the others), uniform tiles in between, all of it in
+// whole waves of the resident warp slots.
+static RingArgs plan_ring_peer(const ldc_grid &g, bool has_prev, bool has_next, int warps_per_sm)
+{
+    struct Key { int nx, rows, prev, next, wps; };
+    static thread_local Key last_key{0, 0, 0, 0, 0};
+    static thread_local RingArgs last;
+    if (last_key.nx == g.nx && last_key.rows == g.row_count && last_key.prev == (int)has_prev &&
+        last_key.next == (int)has_next && last_key.wps == warps_per_sm)
+        return last;
+    RingArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ring_strips(g.nx, &ra.n_strips, &ra.cols);
+    const long slots = (long)warps_per_sm * sm_count();
+    const int n_edges = (has_prev ? 1 : 0) + (has_next ? 1 : 0);
+    const int edge = ring_edge_rows(g, n_edges);
+    const int mid = g.row_count - n_edges * edge;
+    const int extra = edge ? n_edges : 0;
+    double best = -1.0;
+    ra.rows = mid;
+    ra.n_row_tiles = 1 + extra;
+    for (int rows = (mid < 4 ? mid : 4); rows <= 128 && rows <= mid; ++rows) {
+        const int tiles = (mid + rows - 1) / rows + extra;
+        const long items = (long)ra.n_strips * tiles;
+        const long waves = (items + slots - 1) / slots;
+        const double balance = (double)items / (double)(waves * slots);
+        const double score = balance * (double)rows / ((double)rows + 2.0);
+        if (score > best) {
+            best = score;
+            ra.rows = rows;
+            ra.n_row_tiles = tiles;
+        }
+    }
+    ra.edge_prev = has_prev ? edge : 0;
+    ra.edge_next = has_next ? edge : 0;
+    ra.per_instance = (long)ra.n_strips * ra.n_row_tiles;
+    ra.total = ra.per_instance;
+    ra.u_total = instance_strides(g).u;
+    ra.debug = ring_tuning().debug;
+    last_key = Key{g.nx, g.row_count, (int)has_prev, (int)has_next, warps_per_sm};
+    last = ra;
+    return ra;
+}
+
+// one launch of the ring kernel
+static int ring_launch(const ldc_grid &g, const RingArgs &ra, const RingGhost &gh, bool peer, const double *X,
+                       const double *U_base, const double *V_old, double *F, double *partials, cudaStream_t s)
+{
+    const bool pow2 = is_pow2_double(g.dx) && is_pow2_double(g.dy);
+    const bool fast = pow2 && g.rho == 1.0 && g.mi == 1.0;
+    RingLaunch *rl = nullptr;
+    if (int rc = ring_launch_for(pow2, fast, g.use_cds != 0, partials != nullptr, peer, &rl)) return rc;
+    const RingPhys rp = ring_phys(g);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)((ra.total + rl->cfg.warps - 1) / rl->cfg.warps));
+    cfg.blockDim = dim3(rl->cfg.warps * 32);
+    cfg.dynamicSmemBytes = rl->smem;
+    cfg.stream = s;
+    // programmatic stream serialization: back-to-back evaluations overlap their launch latency and
+    // tails (see the griddepcontrol pair in the kernel)
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = ring_tuning().pdl ? 1 : 0;
+    LDC_CUDA(cudaLaunchKernelEx(&cfg, rl->fn, g, rp, ra, gh, X, U_base, V_old, F, partials));
+    return LDC_OK;
+}
+
+static int ring_warps_per_sm(const ldc_grid &g, bool norm, bool peer, int *out)
+{
+    const bool pow2 = is_pow2_double(g.dx) && is_pow2_double(g.dy);
+    const bool fast = pow2 && g.rho == 1.0 && g.mi == 1.0;
+    RingLaunch *rl = nullptr;
+    if (int rc = ring_launch_for(pow2, fast, g.use_cds != 0, norm, peer, &rl)) return rc;
+    *out = rl->blocks_per_sm * rl->cfg.warps;
+    return LDC_OK;
 }
 
 static long cell_blocks(const ldc_grid &g) { return ((long)g.nx * g.row_count + 255) / 256; }
@@ -1094,7 +1187,7 @@ extern "C" int64_t ldc_residual_work_doubles(const ldc_grid *g)
     // min(4, row_count) rows unless LDC_RING_ROWS says so
     const int min_rows = ring_tuning().rows > 0 ? ring_tuning().rows : 4;
     const long strips = (g->nx + ring::kCols - 1) / ring::kCols + 1;
-    const long e = strips * ((g->row_count + min_rows - 1) / min_rows);
+    const long e = strips * ((g->row_count + min_rows - 1) / min_rows + 2);   // + two short edge tiles (peer)
     if (b > a) a = b;
     if (c > a) a = c;
     if (d > a) a = d;
@@ -1120,24 +1213,13 @@ extern "C" int ldc_residual(const ldc_grid *g, const double *X_dev, const double
     if (variant == 4 && !ring_eligible(*g, X_dev, U_old_dev, V_old_dev, F_dev)) variant = 2;
     if (variant == 3 && !tma_ok) variant = 2;
     if (variant == 4) {
-        const bool fast = pow2 && g->rho == 1.0 && g->mi == 1.0;
-        RingLaunch *rl = nullptr;
-        if (int rc = ring_launch_for(pow2, fast, g->use_cds != 0, partials != nullptr, &rl)) return rc;
-        const RingArgs ra = plan_ring(*g, rl->blocks_per_sm * rl->cfg.warps);
-        const RingPhys rp = ring_phys(*g);
+        int wps = 0;
+        if (int rc = ring_warps_per_sm(*g, partials != nullptr, false, &wps)) return rc;
+        const RingArgs ra = plan_ring(*g, wps);
         per_instance = ra.per_instance;
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3((unsigned)((ra.total + rl->cfg.warps - 1) / rl->cfg.warps));
-        cfg.blockDim = dim3(rl->cfg.warps * 32);
-        cfg.dynamicSmemBytes = rl->smem;
-        cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = ring_tuning().pdl ? 1 : 0;
-        LDC_CUDA(cudaLaunchKernelEx(&cfg, rl->fn, *g, rp, ra, X_dev, U_old_dev, V_old_dev, F_dev, partials));
+        RingGhost no_ghost;
+        memset(&no_ghost, 0, sizeof(no_ghost));
+        if (int rc = ring_launch(*g, ra, no_ghost, false, X_dev, U_old_dev, V_old_dev, F_dev, partials, s)) return rc;
     } else if (variant == 3) {
         const MarchPlan pl = plan_tma(*g);
         per_instance = (long)pl.grid.x * pl.grid.y;
@@ -1204,28 +1286,112 @@ extern "C" int ldc_residual(const ldc_grid *g, const double *X_dev, const double
     return LDC_OK;
 }
 
+namespace ldc {
+// Halo push of one strip: block 0 moves the strip's first owned row into the ghost row above the
+// previous strip's last row, block 1 the last owned row into the ghost row below the next strip's
+// first row (peer-mapped memory), then publishes the evaluation number in the neighbour's flag word
+// (release at system scope).  One warp per direction and almost no registers, so that the block
+// finds room on an SM next to the resident residual blocks (a 512-thread version had to wait for
+// a residual block to retire and delivered every halo an evaluation late); the data moves as bulk
+// async copies: global -> shared memory -> peer global, 32 KB at a time.
+static constexpr uint32_t kPushChunk = 32768;
+__global__ void __launch_bounds__(32)
+halo_push_kernel(const double *__restrict__ X, long row_doubles, long last_row_offset, ldc_peer_halo peer)
+{
+    extern __shared__ __align__(128) unsigned char push_smem[];
+    const bool up = blockIdx.x == 1;
+    double *dst = up ? peer.next_ghost : peer.prev_ghost;
+    unsigned long long *flag = up ? peer.next_flag : peer.prev_flag;
+    if (!dst) return;
+    const double *src = X + (up ? last_row_offset : 0);
+    const size_t bytes = sizeof(double) * (size_t)row_doubles;
+    if (((((uintptr_t)src) | ((uintptr_t)dst)) & 15) == 0 && (bytes & 15) == 0) {
+        if (threadIdx.x == 0) {
+            uint64_t *bar = reinterpret_cast<uint64_t *>(push_smem + kPushChunk);
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            uint32_t parity = 0;
+            for (size_t off = 0; off < bytes; off += kPushChunk, parity ^= 1u) {
+                const uint32_t n = (uint32_t)((bytes - off < kPushChunk) ? bytes - off : kPushChunk);
+                mbar_expect_tx(bar, n);
+                bulk_g2s(push_smem, reinterpret_cast<const unsigned char *>(src) + off, n, bar);
+                mbar_wait(bar, parity);
+                bulk_s2g(reinterpret_cast<unsigned char *>(dst) + off, push_smem, n);
+                bulk_commit();
+                bulk_wait_all();   // the chunk has reached the neighbour (and shared memory is free again)
+            }
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(peer.epoch) : "memory");
+        }
+    } else {
+        for (long k = threadIdx.x; k < row_doubles; k += 32) dst[k] = src[k];
+        __threadfence_system();
+        __syncwarp();
+        if (threadIdx.x == 0)
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(peer.epoch) : "memory");
+    }
+}
+
+static int validate_peer(const ldc_grid *g, const ldc_peer_halo *peer, const char *who)
+{
+    LDC_REQUIRE(peer, "%s: null peer description", who);
+    LDC_REQUIRE(g->batch == 1, "%s: batch must be 1", who);
+    const bool has_prev = g->row_begin > 0, has_next = g->row_begin + g->row_count < g->ny;
+    LDC_REQUIRE(has_prev == (peer->prev_ghost != nullptr) && has_next == (peer->next_ghost != nullptr),
+                "%s: prev_ghost/next_ghost must be set exactly where a neighbour strip exists", who);
+    LDC_REQUIRE((!has_prev || peer->prev_flag) && (!has_next || peer->next_flag) &&
+                    (peer->my_flags || (!has_prev && !has_next)),
+                "%s: missing flag words", who);
+    LDC_REQUIRE(peer->epoch > 0, "%s: epoch starts at 1", who);
+    return LDC_OK;
+}
+}  // namespace ldc
+
+extern "C" int ldc_residual_peer_push(const ldc_grid *g, const ldc_peer_halo *peer, const double *X_dev,
+                                      void *stream)
+{
+    if (int rc = validate_grid(g, false)) return rc;
+    if (int rc = validate_peer(g, peer, "ldc_residual_peer_push")) return rc;
+    LDC_REQUIRE(X_dev, "ldc_residual_peer_push: null device pointer");
+    if (!peer->prev_ghost && !peer->next_ghost) return LDC_OK;   // a strip without neighbours
+    const long row = 3L * g->nx;
+    halo_push_kernel<<<2, 32, kPushChunk + 16, (cudaStream_t)stream>>>(X_dev, row, row * (g->row_count - 1), *peer);
+    LDC_CHECK_LAUNCH();
+    return LDC_OK;
+}
+
 extern "C" int ldc_residual_peer(const ldc_grid *g, const ldc_peer_halo *peer, const double *X_dev,
                                  const double *U_old_dev, const double *V_old_dev, double *F_dev,
                                  double *norm2_dev, double *work_dev, void *stream)
 {
     if (int rc = validate_grid(g, false)) return rc;
-    LDC_REQUIRE(peer, "ldc_residual_peer: null peer description");
+    if (int rc = validate_peer(g, peer, "ldc_residual_peer")) return rc;
     LDC_REQUIRE(X_dev && U_old_dev && V_old_dev && F_dev, "ldc_residual_peer: null device pointer");
     LDC_REQUIRE(X_dev != F_dev, "ldc_residual_peer: F must not alias X");
     LDC_REQUIRE(!norm2_dev || work_dev, "ldc_residual_peer: norm2 requested without work buffer");
-    LDC_REQUIRE(g->batch == 1, "ldc_residual_peer: batch must be 1");
-    LDC_REQUIRE((g->row_begin > 0) == (peer->prev_row != nullptr) &&
-                    (g->row_begin + g->row_count < g->ny) == (peer->next_row != nullptr),
-                "ldc_residual_peer: prev_row/next_row must be set exactly where a neighbour strip exists");
-    LDC_REQUIRE((!peer->prev_row || peer->prev_flag) && (!peer->next_row || peer->next_flag) &&
-                    (peer->my_flags || (!peer->prev_row && !peer->next_row)),
-                "ldc_residual_peer: missing flag words");
-    LDC_REQUIRE(peer->epoch > 0, "ldc_residual_peer: epoch starts at 1");
+    const bool has_prev = peer->prev_ghost != nullptr, has_next = peer->next_ghost != nullptr;
     cudaStream_t s = (cudaStream_t)stream;
     const bool pow2 = is_pow2_double(g->dx) && is_pow2_double(g->dy);
     const bool fast = pow2 && g->rho == 1.0 && g->mi == 1.0;
     double *partials = norm2_dev ? work_dev : nullptr;
-    const MarchPlan pl = plan_march_peer(*g, peer->prev_row != nullptr, peer->next_row != nullptr);
+    if (ring_eligible(*g, X_dev, U_old_dev, V_old_dev, F_dev)) {
+        int wps = 0;
+        if (int rc = ring_warps_per_sm(*g, partials != nullptr, true, &wps)) return rc;
+        const RingArgs ra = plan_ring_peer(*g, has_prev, has_next, wps);
+        RingGhost gh;
+        memset(&gh, 0, sizeof(gh));
+        gh.prev_word = has_prev ? peer->my_flags + 0 : nullptr;
+        gh.next_word = has_next ? peer->my_flags + 1 : nullptr;
+        gh.epoch = peer->epoch;
+        gh.status = peer->status_dev;
+        if (int rc = ring_launch(*g, ra, gh, true, X_dev, U_old_dev, V_old_dev, F_dev, partials, s)) return rc;
+        if (norm2_dev) {
+            sum_partials_kernel<<<1, 256, 0, s>>>(partials, ra.per_instance, norm2_dev);
+            LDC_CHECK_LAUNCH();
+        }
+        return LDC_OK;
+    }
+    const MarchPlan pl = plan_march_peer(*g, has_prev, has_next);
     const int edge_arg = pl.edge_rows;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1236,8 +1402,7 @@ extern "C" int ldc_residual_peer(const ldc_grid *g, const ldc_peer_halo *peer, c
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    static const bool no_pdl = getenv("LDC_NO_PDL") != nullptr;
-    cfg.numAttrs = no_pdl ? 0 : 1;
+    cfg.numAttrs = ring_tuning().pdl ? 1 : 0;
     const int rows_arg = pl.rows_per_tile;
 #define LDC_LAUNCH_PEER(P2, FA, CD)                                                                   \
     LDC_CUDA(cudaLaunchKernelEx(&cfg, residual_march_peer_kernel<P2, FA, CD>, *g, *peer, X_dev,       \
@@ -1257,5 +1422,68 @@ extern "C" int ldc_residual_peer(const ldc_grid *g, const ldc_peer_halo *peer, c
         sum_partials_kernel<<<1, 256, 0, s>>>(partials, (long)pl.grid.x * pl.grid.y, norm2_dev);
         LDC_CHECK_LAUNCH();
     }
+    return LDC_OK;
+}
+
+// ---- one overlapped evaluation per call: halo push on the context's side stream, kernel on `stream`
+struct ldc_peer_ctx {
+    static constexpr int kEvents = 16;
+    cudaStream_t side = nullptr;
+    cudaEvent_t events[kEvents] = {};
+    long counter = 0;
+    int lag = 4;
+};
+
+extern "C" int ldc_peer_ctx_create(int32_t lag, ldc_peer_ctx **out)
+{
+    LDC_REQUIRE(out, "ldc_peer_ctx_create: null output");
+    LDC_REQUIRE(lag >= 1 && lag < ldc_peer_ctx::kEvents, "ldc_peer_ctx_create: lag must be in 1..%d",
+                ldc_peer_ctx::kEvents - 1);
+    ldc_peer_ctx *c = new ldc_peer_ctx();
+    c->lag = lag;
+    int lo = 0, hi = 0;
+    cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically smallest = highest priority
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi);
+    for (int k = 0; k < ldc_peer_ctx::kEvents && e == cudaSuccess; ++k)
+        e = cudaEventCreateWithFlags(&c->events[k], cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        ldc_peer_ctx_destroy(c);
+        return ldc::cuda_fail(e, "ldc_peer_ctx_create", __FILE__, __LINE__);
+    }
+    *out = c;
+    return LDC_OK;
+}
+
+extern "C" void ldc_peer_ctx_destroy(ldc_peer_ctx *c)
+{
+    if (!c) return;
+    for (int k = 0; k < ldc_peer_ctx::kEvents; ++k)
+        if (c->events[k]) cudaEventDestroy(c->events[k]);
+    if (c->side) cudaStreamDestroy(c->side);
+    delete c;
+}
+
+extern "C" int ldc_residual_peer_step(ldc_peer_ctx *c, const ldc_grid *g, const ldc_peer_halo *peer,
+                                      const double *X_dev, const double *U_old_dev, const double *V_old_dev,
+                                      double *F_dev, double *norm2_dev, double *work_dev, void *stream)
+{
+    LDC_REQUIRE(c, "ldc_residual_peer_step: null context");
+    const long i = c->counter++;
+    static const int dbg = ring_env_int("LDC_PEER_DEBUG", 0);
+    // Flow control: push(i) waits for the residual kernel of evaluation i-lag of THIS strip.  That
+    // kernel needed the neighbours' push(i-lag), which in turn waited for their kernels of
+    // evaluation i-2*lag: when push(i) overwrites a ghost row, the neighbour has finished every
+    // evaluation up to i-2*lag, so rotating more than 2*lag X buffers is safe -- and the event
+    // waited for is `lag` evaluations old, so the pushes are never held up in steady state.
+    if (i >= c->lag && !(dbg & 64))
+        LDC_CUDA(cudaStreamWaitEvent(c->side, c->events[(i - c->lag) % ldc_peer_ctx::kEvents], 0));
+    if (!(dbg & 16))
+        if (int rc = ldc_residual_peer_push(g, peer, X_dev, c->side)) return rc;
+    if (dbg & 128) {   // experiment: the plain kernel on the local ghost rows instead of the peer kernel
+        if (int rc = ldc_residual(g, X_dev, U_old_dev, V_old_dev, F_dev, norm2_dev, work_dev, 0, stream)) return rc;
+    } else if (int rc = ldc_residual_peer(g, peer, X_dev, U_old_dev, V_old_dev, F_dev, norm2_dev, work_dev, stream)) {
+        return rc;
+    }
+    if (!(dbg & 64)) LDC_CUDA(cudaEventRecord(c->events[i % ldc_peer_ctx::kEvents], (cudaStream_t)stream));
     return LDC_OK;
 }

@@ -38,8 +38,12 @@ constexpr int warp_doubles(int depth, bool bulk_store)
 struct RingArgs {
     int n_strips, cols;          // column strips per row, writer columns per strip (even, <= 62)
     int n_row_tiles, rows;       // row tiles per instance, rows per tile
+    int edge_prev, edge_next;    // rows of the short tiles next to a neighbour strip (peer kernel; else 0)
     long per_instance, total;    // work items (warps) per instance / in total
     long u_total;                // doubles in U_old over the whole batch (over-read guard)
+    long u_off;                  // U_old index of the call's first row relative to the (16-byte aligned) U_old base
+    long partial_off;            // first slot of this launch in the sum(F^2) partials
+    int debug;                   // peer kernel experiments: 1 = no flag waits
 };
 
 // Per-cavity constants, evaluated on the host with the IEEE operations the device helpers use
@@ -117,6 +121,40 @@ __device__ __forceinline__ void st_f64x2(double *p, double a, double b)
     asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
 
+// ldc_residual_peer: the ghost rows X[-1] / X[row_count] of a strip are pushed into the local buffer
+// by the neighbour strips (halo_push_kernel, residual.cu), which then store the evaluation number
+// into this strip's flag words.  A warp whose tile needs a ghost row waits (bounded) for the word
+// before it starts its tile -- local memory in both cases.  (The wait sits in the kernel body, not
+// in the tile function: a divergent spin loop next to the ring bookkeeping made ptxas keep the
+// ring slots / copy addresses of EVERY tile flavour in vector registers: 168 registers instead of
+// 138 and a 15 % slower kernel.)
+struct RingGhost {
+    const unsigned long long *prev_word, *next_word;   // my_flags[0] / my_flags[1]; nullptr: no neighbour
+    unsigned long long epoch;                          // evaluation number the words must have reached
+    int32_t *status;
+};
+
+__device__ __forceinline__ unsigned long long ld_flag_acquire(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// bounded wait (a few seconds): a lost neighbour must not hang the device.  On success the ghost
+// row is ordered before the bulk copy that follows (acquire, then generic -> async proxy fence).
+__device__ __forceinline__ void wait_ghost(const unsigned long long *word, unsigned long long epoch,
+                                           int32_t *status)
+{
+    for (long it = 0; it < (1L << 24); ++it) {
+        if (ld_flag_acquire(word) >= epoch) {
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            return;
+        }
+        __nanosleep(it < 64 ? 20 : 250);
+    }
+    if (status) atomicExch(status, 1);
+}
+
 struct Cell2 {   // the two cells of a lane and the cell east of them: raw slots of one grid row
     double aP, aU, aV, bP, bU, bV, eP, eU, eV;
 };
@@ -191,6 +229,7 @@ __device__ __forceinline__ double ring_tile(const ldc_grid &g, const RingPhys &r
     // ---- consumer state
     int slot = 0;
     uint32_t parity = 0;
+    auto wait_slot = [&]() { mbar_wait(bars + slot, parity); };
     auto next_slot = [&]() {
         if (++slot == DEPTH) {
             slot = 0;
@@ -239,10 +278,10 @@ __device__ __forceinline__ double ring_tile(const ldc_grid &g, const RingPhys &r
     Cell2 C;                         // current row, masked
     double rawU_b, rawV_a, rawV_b;   // its raw dummy slots (rows F = X)
     {
-        mbar_wait(bars + slot, parity);
+        wait_slot();
         Cell2 S = read_row(row_ok(jl0 - 1));
         next_slot();
-        mbar_wait(bars + slot, parity);
+        wait_slot();
         C = read_row(true);
         next_slot();
         const int jg = g.row_begin + jl0;
@@ -272,7 +311,7 @@ __device__ __forceinline__ double ring_tile(const ldc_grid &g, const RingPhys &r
 #pragma unroll 2
     for (int jl = jl0; jl < jl1; ++jl, frow += 3L * nx, u_rd += nx - 1) {
         const int jg = g.row_begin + jl;
-        mbar_wait(bars + slot, parity);
+        wait_slot();
         const double *stg = stages + slot * ring::kStage;
         Cell2 N = read_row(row_ok(jl + 1));
         const double NrawU_b = N.bU, NrawV_a = N.aV, NrawV_b = N.bV;
@@ -411,12 +450,52 @@ __device__ __forceinline__ double ring_tile(const ldc_grid &g, const RingPhys &r
     return sq;
 }
 
-template <bool POW2, bool FAST, bool CDS, bool NORM, bool BULK_STORE, int WARPS, int DEPTH, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB)
-residual_ring_kernel(const ldc_grid g, const RingPhys rp, const RingArgs ra, const double *__restrict__ X,
-                     const double *__restrict__ U_old, const double *__restrict__ V_old,
-                     double *__restrict__ F, double *__restrict__ partials)
+// work item -> tile.  Row tiles: uniform `rows` tall, except that a strip with a neighbour
+// (peer kernel) starts / ends with a SHORT tile of edge_prev / edge_next rows; those two come
+// first in the work order so that their NVLink round trips overlap everything else.
+struct RingTile {
+    int inst, c0, cw, jl0, jl1;
+};
+__device__ __forceinline__ RingTile ring_decode(const ldc_grid &g, const RingArgs &ra, long w)
 {
+    RingTile t;
+    t.inst = (int)(w / ra.per_instance);
+    const int r = (int)(w - (long)t.inst * ra.per_instance);
+    int rt = r / ra.n_strips;
+    const int strip = r - rt * ra.n_strips;
+    t.c0 = strip * ra.cols;
+    t.cw = min(ra.cols, g.nx - t.c0);
+    const int n_edges = (ra.edge_prev ? 1 : 0) + (ra.edge_next ? 1 : 0);
+    if (ra.edge_prev && rt == 0) {
+        t.jl0 = 0;
+        t.jl1 = ra.edge_prev;
+    } else if (ra.edge_next && rt == (ra.edge_prev ? 1 : 0)) {
+        t.jl0 = g.row_count - ra.edge_next;
+        t.jl1 = g.row_count;
+    } else {
+        rt -= n_edges;
+        t.jl0 = ra.edge_prev + rt * ra.rows;
+        t.jl1 = min(t.jl0 + ra.rows, g.row_count - ra.edge_next);
+    }
+    return t;
+}
+
+// PEER = false: the residual kernel of ldc_residual.
+// PEER = true : ldc_residual_peer.  The ghost rows next to a neighbour strip arrive in the LOCAL
+// buffer through the neighbours' halo_push_kernel; a warp whose tile touches the strip's first /
+// last owned row waits (acquire, bounded) until its flag word shows the evaluation number and
+// then runs its tile on local memory.  Edge tiles are short and first in the work order.  The
+// kernel performs no remote access on purpose: a kernel that stores to peer memory pays a
+// system-scope flush of ~2.7 us at its end (measured), and a spin loop inside the tile function
+// costs every tile flavour registers (168 instead of 138).
+// MAXREG: register cap per thread; up to 168 keep three 4-warp blocks (12 warps) resident per SM.
+template <bool POW2, bool FAST, bool CDS, bool NORM, bool PEER, int WARPS, int DEPTH, int MAXREG>
+__global__ void __launch_bounds__(WARPS * 32) __maxnreg__(MAXREG)
+residual_ring_kernel(const ldc_grid g, const RingPhys rp, const RingArgs ra, const RingGhost gh,
+                     const double *__restrict__ X, const double *__restrict__ U_old,
+                     const double *__restrict__ V_old, double *__restrict__ F, double *__restrict__ partials)
+{
+    constexpr bool BULK_STORE = false;
     extern __shared__ __align__(128) double ring_smem[];
     // let the next kernel of the stream start launching (programmatic dependent launch)
     asm volatile("griddepcontrol.launch_dependents;");
@@ -425,35 +504,43 @@ residual_ring_kernel(const ldc_grid g, const RingPhys rp, const RingArgs ra, con
     const int lane = threadIdx.x & 31;
     const long w = (long)blockIdx.x * WARPS + warp;      // work item of this warp
     if (w >= ra.total) return;
-    const int inst = (int)(w / ra.per_instance);
-    const int r = (int)(w - (long)inst * ra.per_instance);
-    const int rt = r / ra.n_strips, strip = r - rt * ra.n_strips;
+    const RingTile t = ring_decode(g, ra, w);
     const Strides st = instance_strides(g);
-    X += inst * st.x;
-    F += inst * st.x;
-    V_old += inst * st.v;
-    const int c0 = strip * ra.cols;
-    const int cw = min(ra.cols, g.nx - c0);
-    const int jl0 = rt * ra.rows;
-    const int jl1 = min(jl0 + ra.rows, g.row_count);
+    X += t.inst * st.x;
+    F += t.inst * st.x;
+    V_old += t.inst * st.v;
+    double *smem = ring_smem + (size_t)warp * ring::warp_doubles(DEPTH, BULK_STORE);
     // do not touch global memory before every kernel queued ahead of us has completed
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const double bc = g.bc_dev ? g.bc_dev[inst] : rp.bc;
-    const double vol_dt = g.dt_dev ? ddiv(dmul(rp.dx, rp.dy), g.dt_dev[inst]) : rp.vol_dt;
-    double *smem = ring_smem + (size_t)warp * ring::warp_doubles(DEPTH, BULK_STORE);
+    const double bc = g.bc_dev ? g.bc_dev[t.inst] : rp.bc;
+    const double vol_dt = g.dt_dev ? ddiv(dmul(rp.dx, rp.dy), g.dt_dev[t.inst]) : rp.vol_dt;
+    const int jg0 = g.row_begin + t.jl0, jg1 = g.row_begin + t.jl1;
+    bool edge = false;
+    if (PEER) {
+        const bool needs_prev = t.jl0 == 0 && gh.prev_word != nullptr;
+        const bool needs_next = t.jl1 == g.row_count && gh.next_word != nullptr;
+        edge = needs_prev || needs_next;
+        if (edge && !(ra.debug & 1)) {
+            if (lane == 0) {
+                if (needs_prev) wait_ghost(gh.prev_word, gh.epoch, gh.status);
+                if (needs_next) wait_ghost(gh.next_word, gh.epoch, gh.status);
+            }
+            __syncwarp();
+        }
+    }
     // warp-uniform: no lane touches a wall, the lid, a dummy slot or a missing ghost row
-    const int jg0 = g.row_begin + jl0, jg1 = g.row_begin + jl1;
-    const bool interior = c0 >= 2 && c0 + cw + 1 <= g.nx - 1 && jg0 >= 1 && jg1 <= g.ny - 2;
+    const bool interior = t.c0 >= 2 && t.c0 + t.cw + 1 <= g.nx - 1 && jg0 >= 1 && jg1 <= g.ny - 2 && !edge;
+    const long u_off = t.inst * st.u + ra.u_off;
     double sq;
     if (interior)
-        sq = ring_tile<POW2, FAST, CDS, true, NORM, BULK_STORE, DEPTH>(g, rp, vol_dt, bc, ra, X, U_old, V_old, F,
-                                                                      inst * st.u, smem, lane, c0, cw, jl0, jl1);
+        sq = ring_tile<POW2, FAST, CDS, true, NORM, BULK_STORE, DEPTH>(g, rp, vol_dt, bc, ra, X, U_old, V_old, F, u_off,
+                                                                      smem, lane, t.c0, t.cw, t.jl0, t.jl1);
     else
-        sq = ring_tile<POW2, FAST, CDS, false, NORM, BULK_STORE, DEPTH>(g, rp, vol_dt, bc, ra, X, U_old, V_old, F,
-                                                                       inst * st.u, smem, lane, c0, cw, jl0, jl1);
+        sq = ring_tile<POW2, FAST, CDS, false, NORM, BULK_STORE, DEPTH>(g, rp, vol_dt, bc, ra, X, U_old, V_old, F, u_off,
+                                                                       smem, lane, t.c0, t.cw, t.jl0, t.jl1);
     if (NORM) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        if (lane == 0) partials[w] = sq;
+        if (lane == 0) partials[ra.partial_off + w] = sq;
     }
 }

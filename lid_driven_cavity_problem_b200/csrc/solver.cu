@@ -254,6 +254,49 @@ static ldc_grid level_grid(const ldc_solver *s, const MgLevel &l)
     return g;
 }
 
+namespace ldc {
+// Shape of the multigrid hierarchy of the cavity / row strip `g`: number of levels and the first
+// replicated level (-1: none).  Host arithmetic only (ldc_solver_plan_levels exposes it so that
+// the partition rules can be tested without a device).
+static void plan_levels(const ldc_grid *g, const ldc_solver_options &o, int *nlev_out, int *l_rep_out)
+{
+    long kRepCells = 32768;
+    if (const char *env = getenv("LDC_REP_CELLS")) kRepCells = atol(env) > 0 ? atol(env) : kRepCells;
+    const bool strip = !(g->row_begin == 0 && g->row_count == g->ny);
+    int nlev = 1, l_rep = -1;
+    if (o.pc_type == LDC_PC_MG_VANKA) {
+        int nx = g->nx, ny = g->row_count, rb = g->row_begin, nyg = g->ny;
+        const int min_size = o.mg_min_size > 2 ? o.mg_min_size : 3;
+        bool rep = false;
+        while ((o.mg_levels <= 0 || nlev < o.mg_levels) && nx % 2 == 0 && nyg % 2 == 0 && nx / 2 >= min_size) {
+            if (!rep) {
+                if (ny % 2 != 0 || rb % 2 != 0) break;
+                if (strip && ((long)(nx / 2) * (nyg / 2) <= kRepCells || ny / 2 < 2)) {
+                    if (ny / 2 < 1) break;
+                    rep = true;
+                    l_rep = nlev;
+                } else if (!strip && ny / 2 < min_size) break;
+            } else if (nyg / 2 < min_size) break;
+            nx /= 2; ny /= 2; rb /= 2; nyg /= 2; ++nlev;
+        }
+    }
+    *nlev_out = nlev;
+    *l_rep_out = l_rep;
+}
+}  // namespace ldc
+
+extern "C" int ldc_solver_plan_levels(const ldc_grid *g, const ldc_solver_options *opt, int32_t *levels_out,
+                                      int32_t *replicated_from_out)
+{
+    if (int rc = validate_grid(g, false)) return rc;
+    LDC_REQUIRE(opt && levels_out && replicated_from_out, "ldc_solver_plan_levels: null argument");
+    int nlev = 1, l_rep = -1;
+    ldc::plan_levels(g, *opt, &nlev, &l_rep);
+    *levels_out = nlev;
+    *replicated_from_out = l_rep;
+    return LDC_OK;
+}
+
 extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *opt, ldc_solver **out)
 {
     LDC_REQUIRE(out != nullptr, "ldc_solver_create: out is NULL");
@@ -310,25 +353,8 @@ extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *op
     // right-hand side is all-gathered and every rank continues the cycle on the full coarse grid.
     // That keeps the latency-bound coarse levels free of halo exchanges and makes them identical to
     // the single-GPU hierarchy.
-    long kRepCells = 32768;
-    if (const char *env = getenv("LDC_REP_CELLS")) kRepCells = atol(env) > 0 ? atol(env) : kRepCells;
     int nlev = 1, l_rep = -1;
-    if (o.pc_type == LDC_PC_MG_VANKA) {
-        int nx = g->nx, ny = g->row_count, rb = g->row_begin, nyg = g->ny;
-        const int min_size = o.mg_min_size > 2 ? o.mg_min_size : 3;
-        bool rep = false;
-        while ((o.mg_levels <= 0 || nlev < o.mg_levels) && nx % 2 == 0 && nyg % 2 == 0 && nx / 2 >= min_size) {
-            if (!rep) {
-                if (ny % 2 != 0 || rb % 2 != 0) break;
-                if (s->strip && ((long)(nx / 2) * (nyg / 2) <= kRepCells || ny / 2 < 2)) {
-                    if (ny / 2 < 1) break;
-                    rep = true;
-                    l_rep = nlev;
-                } else if (!s->strip && ny / 2 < min_size) break;
-            } else if (nyg / 2 < min_size) break;
-            nx /= 2; ny /= 2; rb /= 2; nyg /= 2; ++nlev;
-        }
-    }
+    plan_levels(g, o, &nlev, &l_rep);
     s->levels.resize(nlev);
     for (int l = 0; l < nlev && rc == LDC_OK; ++l) {
         MgLevel &L = s->levels[l];
@@ -414,7 +440,7 @@ extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *op
     A(s->dalloc(&s->ks.hnext, B));
     A(s->dalloc(&s->run_dev, B));
     A(s->dalloc(&s->fin_dev, B));
-    A(s->dalloc(&s->scal_dev, (size_t)3 * B));
+    A(s->dalloc(&s->scal_dev, (size_t)3 * B + 8));   // + room for the shape agreement of set_comm
     A(s->halloc(&s->scal_host, (size_t)3 * B));
     A(s->halloc(&s->res_host, B));
     A(s->halloc(&s->du_host, B));
@@ -460,6 +486,32 @@ extern "C" int ldc_solver_set_comm(ldc_solver *s, const ldc_comm_ops *ops)
     LDC_REQUIRE(s && ops && ops->halo_exchange && ops->allreduce && ops->allgather,
                 "ldc_solver_set_comm: incomplete function table");
     LDC_REQUIRE(s->batch == 1, "a distributed solver holds one cavity");
+    // The hierarchy (levels, replication level), the Krylov limits derived from it and the
+    // all-gather layout (rank r's piece at r*count) were decided from THIS rank's row_begin /
+    // row_count.  Ranks that disagree would issue different sequences of collectives and hang, so
+    // agree here, collectively: every rank sees the minimum and maximum of each quantity and all
+    // of them refuse a partition that is not uniform.
+    {
+        int l_rep = -1;
+        for (size_t l = 0; l < s->levels.size(); ++l)
+            if (s->levels[l].replicated) { l_rep = (int)l; break; }
+        const double mine[3] = {(double)s->levels[0].ny, (double)s->levels.size(), (double)l_rep};
+        double host[6];
+        for (int k = 0; k < 3; ++k) { host[2 * k] = mine[k]; host[2 * k + 1] = -mine[k]; }
+        LDC_CUDA(cudaMemcpy(s->scal_dev, host, sizeof(host), cudaMemcpyHostToDevice));
+        if (int rc = ops->allreduce(ops->ctx, s->scal_dev, 6, 1, nullptr)) {
+            ldc::set_error("ldc_solver_set_comm: all-reduce of the strip shapes failed (%d)", rc);
+            return LDC_ERR_CUDA;
+        }
+        LDC_CUDA(cudaStreamSynchronize(nullptr));
+        LDC_CUDA(cudaMemcpy(host, s->scal_dev, sizeof(host), cudaMemcpyDeviceToHost));
+        static const char *what[3] = {"rows per strip", "multigrid levels", "replication level"};
+        for (int k = 0; k < 3; ++k)
+            LDC_REQUIRE(host[2 * k] == -host[2 * k + 1],
+                        "ldc_solver_set_comm: %s differ across ranks (%g..%g, this rank %g); the row strips "
+                        "must be equal (ny divisible by the number of ranks)",
+                        what[k], -host[2 * k + 1], host[2 * k], mine[k]);
+    }
     s->comm = *ops;
     s->has_comm = true;
     // NCCL point-to-point and all-reduce calls are stream-ordered and can be captured; the

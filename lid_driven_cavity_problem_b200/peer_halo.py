@@ -1,6 +1,8 @@
-"""Row-strip residual with the halo exchange fused into the kernel (``ldc_residual_peer``,
-include/ldc_b200.h): the neighbour strips' boundary rows are read from peer-mapped memory over
-NVLink after an in-kernel flag handshake, so one evaluation is one launch and no collective.
+"""Row-strip residual without a collective (``ldc_residual_peer_push`` + ``ldc_residual_peer``,
+include/ldc_b200.h): every strip pushes its boundary rows into the neighbours' ghost rows over
+NVLink (a small kernel on a side stream) and publishes the evaluation number in their flag
+words; the residual kernel's boundary tiles wait for their own words and read the ghost rows
+from local memory.  One evaluation is one residual launch plus one overlapped push.
 
 The reference has no multi-rank path (sequential PETSc objects only,
 nonlinear_solver/petsc_solver_wrapper.py:75,77,117,125); this is the SURVEY 8(e) strip
@@ -11,7 +13,8 @@ Region layout (identical on every strip, so a neighbour's addresses follow from 
     [0, 16)     two 64-bit flag words: [0] written by strip r-1, [1] by strip r+1
     [64, 68)    status word (1 = a wait timed out)
     [256, ...)  ``n_sets`` X buffers, each ``3*nx*(rows_max+2)`` doubles:
-                [unused ghost row | owned rows | ...]; strips own ``rows`` <= ``rows_max`` rows
+                [ghost row below | owned rows | ghost row above | ...]; a strip owns
+                ``rows`` <= ``rows_max`` rows
 """
 import ctypes
 
@@ -48,6 +51,7 @@ class PeerStripResidual(object):
         self.local, self.prev, self.next = int(local), int(prev or 0), int(next or 0)
         self.prev_rows, self.n_sets = int(prev_rows), int(n_sets)
         self.epoch = 0
+        self._ctx = None
         has_prev = grid.row_begin > 0
         has_next = grid.row_begin + grid.row_count < grid.ny
         if has_prev and not self.prev or has_next and not self.next:
@@ -74,35 +78,77 @@ class PeerStripResidual(object):
         ph = _native.LdcPeerHalo()
         off = HEADER_BYTES + k * self.set_bytes
         if self._has_prev:
-            ph.prev_row = self.prev + off + self.row_bytes * self.prev_rows   # its last owned row
-            ph.prev_flag = self.prev + 8                                      # its my_flags[1]
+            ph.prev_ghost = self.prev + off + self.row_bytes * (self.prev_rows + 1)   # above its last owned row
+            ph.prev_flag = self.prev + 8                                              # its my_flags[1]
         if self._has_next:
-            ph.next_row = self.next + off + self.row_bytes                    # its first owned row
-            ph.next_flag = self.next                                          # its my_flags[0]
+            ph.next_ghost = self.next + off                                           # below its first owned row
+            ph.next_flag = self.next                                                  # its my_flags[0]
         ph.my_flags = self.local
         ph.status_dev = self.local + STATUS_OFFSET
         return ph
 
-    def residual(self, k, U_old, V_old, F, stream=None, norm2=None, work=None):
-        """F <- residual of the strip's owned rows of X buffer ``k``; every strip must make the same
-        sequence of calls (the epoch counter is the handshake)."""
-        self.bind(k, U_old, V_old, F, norm2, work)(stream if stream is not None else _native.current_stream())
-
-    def bind(self, k, U_old, V_old, F, norm2=None, work=None):
-        """``launch(stream)`` for a fixed set of buffers with every argument converted once: the
-        kernel runs for ~20 us, so a hot loop should not rebuild ctypes structures per call"""
+    def bind_overlapped(self, k, U_old, V_old, F, norm2=None, work=None, lag=4):
+        """``launch(stream)``: ONE library call per evaluation (ldc_residual_peer_step) that puts the
+        push on the library's high-priority side stream and the kernel on ``stream``.  For loops
+        over rotating X buffers that are final before the loop starts; needs ``n_sets > 2*lag``
+        (see include/ldc_b200.h)."""
+        if self.n_sets <= 2 * lag:
+            raise ValueError("overlapped evaluation needs more than 2*lag rotating X buffers")
+        if self._ctx is None:
+            self._ctx = ctypes.c_void_p()
+            _native.check(self.lib.ldc_peer_ctx_create(lag, ctypes.byref(self._ctx)), 'ldc_peer_ctx_create')
         ph = self._peer_struct(k)
         ph_ref = ctypes.byref(ph)
-        fn, grid = self.lib.ldc_residual_peer, self.grid
+        fn, grid, ctx = self.lib.ldc_residual_peer_step, self.grid, self._ctx
         args = (ctypes.c_void_p(self.x_address(k)), _native.ptr(U_old), _native.ptr(V_old), _native.ptr(F),
                 _native.ptr(norm2), _native.ptr(work))
-        keep = (U_old, V_old, F, norm2, work)
 
         def launch(stream):
             self.epoch += 1
             ph.epoch = self.epoch
-            rc = fn(grid, ph_ref, args[0], args[1], args[2], args[3], args[4], args[5], stream)
+            rc = fn(ctx, grid, ph_ref, args[0], args[1], args[2], args[3], args[4], args[5], stream)
             if rc != 0:
-                _native.check(rc, 'ldc_residual_peer')
+                _native.check(rc, 'ldc_residual_peer_step')
+        launch.keep = (U_old, V_old, F, norm2, work)
+        return launch
+
+    def close(self):
+        if self._ctx is not None:
+            self.lib.ldc_peer_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def residual(self, k, U_old, V_old, F, stream=None, norm2=None, work=None, push_stream=None):
+        """F <- residual of the strip's owned rows of X buffer ``k`` (push + kernel); every strip must
+        make the same sequence of calls (the epoch counter is the handshake)."""
+        self.bind(k, U_old, V_old, F, norm2, work)(stream if stream is not None else _native.current_stream(),
+                                                   push_stream)
+
+    def bind(self, k, U_old, V_old, F, norm2=None, work=None):
+        """``launch(stream, push_stream=None, push=True, kernel=True)`` for a fixed set of buffers
+        with every argument converted once (the kernel runs for ~14 us, a hot loop should not
+        rebuild ctypes structures per call).  ``push_stream``: where the halo push goes (``None`` =
+        the launch stream, i.e. serialised in front of the kernel).  X of buffer ``k`` must be final
+        on that stream; the caller also keeps pushes from running more than ``n_sets - 2``
+        evaluations ahead of the neighbours (see include/ldc_b200.h)."""
+        ph = self._peer_struct(k)
+        ph_ref = ctypes.byref(ph)
+        fn, push_fn, grid = self.lib.ldc_residual_peer, self.lib.ldc_residual_peer_push, self.grid
+        x_ptr = ctypes.c_void_p(self.x_address(k))
+        args = (x_ptr, _native.ptr(U_old), _native.ptr(V_old), _native.ptr(F), _native.ptr(norm2), _native.ptr(work))
+        keep = (U_old, V_old, F, norm2, work)
+        has_neighbour = self._has_prev or self._has_next
+
+        def launch(stream, push_stream=None, push=True, kernel=True):
+            if push:
+                self.epoch += 1
+            ph.epoch = self.epoch
+            if push and has_neighbour:
+                rc = push_fn(grid, ph_ref, x_ptr, push_stream if push_stream is not None else stream)
+                if rc != 0:
+                    _native.check(rc, 'ldc_residual_peer_push')
+            if kernel:
+                rc = fn(grid, ph_ref, args[0], args[1], args[2], args[3], args[4], args[5], stream)
+                if rc != 0:
+                    _native.check(rc, 'ldc_residual_peer')
         launch.keep = keep
         return launch

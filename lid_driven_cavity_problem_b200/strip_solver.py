@@ -26,10 +26,12 @@ class CudaStripSolver(object):
         lib = _native.lib()
         self.nx, self.ny, self.bc, self.dt = int(nx), int(ny), float(bc), float(dt)
         self.rank, self.world, self.comm = rank, world, comm
-        align = 64
-        while align > 1 and ny % (align * world) != 0:
-            align //= 2
-        self.row_begin, self.row_count = _comm.strip_partition(ny, world, rank, align)
+        if ny % world != 0:
+            # unequal strips would build different multigrid hierarchies per rank (different
+            # sequences of collectives -> a hang); every rank sees the same ny / world, so every
+            # rank refuses.  ldc_solver_set_comm checks the same thing collectively.
+            raise ValueError("row strips must be equal: ny=%d is not divisible by %d ranks" % (ny, world))
+        self.row_begin, self.row_count = _comm.strip_partition(ny, world, rank, self._align(ny, world))
         g = _native.LdcGrid()
         g.nx, g.ny, g.row_begin, g.row_count, g.batch, g.use_cds = nx, ny, self.row_begin, self.row_count, 1, 0
         g.dt, g.dx, g.dy, g.rho, g.mi, g.bc = float(dt), size_x / nx, size_y / ny, float(rho), float(mi), float(bc)
@@ -80,14 +82,16 @@ class CudaStripSolver(object):
         if self.world == 1:
             return X
         import torch.distributed as dist
-        sizes = [3 * self.nx * _comm.strip_partition(self.ny, self.world, r, self._align())[1] for r in range(self.world)]
+        sizes = [3 * self.nx * _comm.strip_partition(self.ny, self.world, r, self._align(self.ny, self.world))[1]
+                 for r in range(self.world)]
         parts = [self._torch.empty(sz, dtype=X.dtype, device='cuda') for sz in sizes]
         dist.all_gather(parts, X)
         return self._torch.cat(parts)
 
-    def _align(self):
+    @staticmethod
+    def _align(ny, world):
         align = 64
-        while align > 1 and self.ny % (align * self.world) != 0:
+        while align > 1 and ny % (align * world) != 0:
             align //= 2
         return align
 

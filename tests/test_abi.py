@@ -117,11 +117,13 @@ def test_argument_validation_happens_before_any_device_work():
     ph = _native.LdcPeerHalo()
     assert refused(lib.ldc_residual_peer(g, ph, px, px, px, pf, None, None, None), b'epoch starts at 1')
     ph.epoch = 1
-    ph.next_row = px          # a full grid has no neighbour strip
+    ph.next_ghost = px        # a full grid has no neighbour strip
     assert refused(lib.ldc_residual_peer(g, ph, px, px, px, pf, None, None, None), b'neighbour strip exists')
     g.batch = 2
     assert refused(lib.ldc_residual_peer(g, ph, px, px, px, pf, None, None, None), b'batch must be 1')
+    assert refused(lib.ldc_residual_peer_push(g, ph, px, None), b'batch must be 1')
     g.batch = 1
+    assert refused(lib.ldc_residual_peer_push(g, ph, px, None), b'neighbour strip exists')
     assert lib.ldc_residual_work_doubles(g) > 0
     if not torch.cuda.is_available():
         rc = lib.ldc_residual(g, px, px, px, pf, None, None, 0, None)

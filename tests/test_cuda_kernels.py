@@ -142,12 +142,17 @@ def test_residual_row_strips(cuda):
 
 
 @pytest.mark.parametrize("nx,ny,bounds", [(96, 70, [0, 17, 18, 40, 70]), (250, 128, [0, 64, 128]),
-                                          (1024, 512, [0, 128, 256, 384, 512])])
+                                          (1024, 512, [0, 128, 256, 384, 512]), (64, 12, [0, 1, 2, 5, 12]),
+                                          (257, 40, [0, 20, 40])])
 def test_residual_peer_halo_strips_one_gpu(cuda, nx, ny, bounds):
-    """ldc_residual_peer: the strips read their neighbours' boundary rows from the neighbours'
-    regions after the in-kernel flag handshake.  Here all strips live on one GPU (one region and
-    one stream each, so the kernels overlap like ranks do); result bit-exact, twice in a row
-    (second epoch on changed X), status word clean."""
+    """ldc_residual_peer_push + ldc_residual_peer: every strip pushes its boundary rows into the
+    neighbours' ghost rows and publishes the evaluation number, the residual kernels wait for the
+    words and read the ghosts locally.  All strips live on one GPU here, so all pushes of an
+    evaluation are launched (and complete, stream order) before the first residual kernel: kernels
+    that wait for each other must not be separate launches on one device.  The overlapped form
+    runs in `bench.py --gpus N`, which compares every strip with a single-GPU evaluation.  Result
+    bit-exact, twice in a row (second epoch on changed X), status word clean.  Odd nx takes the
+    register-prefetch kernel, even nx the ring kernel."""
     from oracle import ldc_oracle as orc
     from lid_driven_cavity_problem_b200 import peer_halo
     torch, native = cuda['torch'], cuda['native']
@@ -158,7 +163,7 @@ def test_residual_peer_halo_strips_one_gpu(cuda, nx, ny, bounds):
     rows_max = max(j1 - j0 for j0, j1 in spans)
     nbytes = peer_halo.region_bytes(nx, rows_max, 1)
     regions = [torch.zeros(nbytes // 8, dtype=torch.float64, device='cuda') for _ in spans]
-    strips, Us, Vs, Fs, streams = [], [], [], [], []
+    strips, Us, Vs, Fs = [], [], [], []
     for r, (j0, j1) in enumerate(spans):
         grid = native.grid_from_graph(g, row_begin=j0, row_count=j1 - j0)
         prev = regions[r - 1].data_ptr() if r > 0 else 0
@@ -167,13 +172,8 @@ def test_residual_peer_halo_strips_one_gpu(cuda, nx, ny, bounds):
         strips.append(peer_halo.PeerStripResidual(grid, regions[r].data_ptr(), prev, nxt, prev_rows, rows_max))
         Us.append(torch.from_numpy(U_old[j0:j1].copy().ravel()).cuda())
         Vl = V_old[j0:min(j1, ny - 1)].copy().ravel()
-        Vs.append(torch.from_numpy(Vl if Vl.size else np.zeros(1)).cuda())
+        Vs.append(torch.from_numpy(Vl if Vl.size else np.zeros(2)).cuda())
         Fs.append(torch.full((3 * nx * (j1 - j0),), np.nan, dtype=torch.float64, device='cuda'))
-        streams.append(torch.cuda.Stream())
-    # all strips share one process here: a lazily loaded kernel (first use of the norm reduction)
-    # would make the host wait for strip 0's kernel, which waits for strip 1's launch -> load it now
-    cuda['crf'].residual_function_device(torch.from_numpy(X).cuda(), g, variant=2,
-                                         norm2_out=torch.zeros(1, dtype=torch.float64, device='cuda'))
     for epoch in range(2):
         Xe = X * (1.0 + 0.25 * epoch)
         F_ref = orc.residual_function(Xe, g)
@@ -183,9 +183,12 @@ def test_residual_peer_halo_strips_one_gpu(cuda, nx, ny, bounds):
         n2 = [torch.zeros(1, dtype=torch.float64, device='cuda') for _ in spans]
         work = [torch.zeros(int(native.lib().ldc_residual_work_doubles(s.grid)), dtype=torch.float64,
                             device='cuda') for s in strips]
-        for r in range(len(spans)):
-            with torch.cuda.stream(streams[r]):
-                strips[r].residual(0, Us[r], Vs[r], Fs[r], norm2=n2[r], work=work[r])
+        launches = [strips[r].bind(0, Us[r], Vs[r], Fs[r], n2[r], work[r]) for r in range(len(spans))]
+        st = native.current_stream()
+        for launch in launches:
+            launch(st, kernel=False)                 # all pushes first ...
+        for launch in launches:
+            launch(st, push=False)                   # ... then the residual kernels
         torch.cuda.synchronize()
         out = np.concatenate([F.cpu().numpy() for F in Fs])
         assert not any(s.status() for s in strips)
@@ -209,7 +212,7 @@ def test_residual_peer_halo_times_out_instead_of_hanging(cuda):
     U = torch.from_numpy(g.ns_x_mesh.phi_old[:(nx - 1) * 16].copy()).cuda()
     V = torch.from_numpy(g.ns_y_mesh.phi_old[:nx * 16].copy()).cuda()
     F = torch.empty(3 * nx * 16, dtype=torch.float64, device='cuda')
-    strip.residual(0, U, V, F)
+    strip.residual(0, U, V, F)     # pushes into the silent neighbour's region, then waits for its word
     assert strip.status()          # timed out, reported, device still alive
     assert torch.isfinite(F[:3 * nx * 8]).all()
 
@@ -226,6 +229,8 @@ def test_residual_peer_rejects_inconsistent_neighbours(cuda):
     ph.epoch = 1
     rc = native.lib().ldc_residual_peer(grid, ph, native.ptr(buf), native.ptr(buf), native.ptr(buf),
                                         buf.data_ptr() + 8 * 4096, None, None, native.current_stream())
+    assert rc != 0 and b'neighbour' in native.lib().ldc_last_error()
+    rc = native.lib().ldc_residual_peer_push(grid, ph, native.ptr(buf), native.current_stream())
     assert rc != 0 and b'neighbour' in native.lib().ldc_last_error()
 
 

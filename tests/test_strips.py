@@ -55,27 +55,40 @@ def test_peer_halo_region_layout_and_handshake_addresses(monkeypatch):
         @staticmethod
         def ldc_residual_peer(grid, ph_ref, X, U, V, F, n2, work, stream):
             ph = ph_ref._obj
-            calls.append((ph.prev_row, ph.next_row, ph.my_flags, ph.prev_flag, ph.next_flag, ph.epoch,
-                          ph.status_dev, X.value))
+            calls.append(('kernel', ph.prev_ghost, ph.next_ghost, ph.my_flags, ph.prev_flag, ph.next_flag, ph.epoch,
+                          ph.status_dev, X.value, stream.value))
+            return 0
+
+        @staticmethod
+        def ldc_residual_peer_push(grid, ph_ref, X, stream):
+            ph = ph_ref._obj
+            calls.append(('push', ph.prev_ghost, ph.next_ghost, ph.my_flags, ph.prev_flag, ph.next_flag, ph.epoch,
+                          ph.status_dev, X.value, stream.value))
             return 0
     local, prev, nxt = 0x100000, 0x200000, 0x300000
     monkeypatch.setattr(_native, 'lib', lambda: FakeLib)
     strip = peer_halo.PeerStripResidual(g, local, prev, nxt, prev_rows=7, rows_max=rows_max, n_sets=n_sets)
     launch = strip.bind(2, None, None, None)
-    launch(ctypes.c_void_p(0))
-    launch(ctypes.c_void_p(0))
+    launch(ctypes.c_void_p(5))
+    launch(ctypes.c_void_p(5), ctypes.c_void_p(9))      # push on a side stream
     off = peer_halo.HEADER_BYTES + 2 * set_b
-    p_row, n_row, flags, p_flag, n_flag, epoch, status, x = calls[-1]
-    assert p_row == prev + off + row_b * 7          # ghost slot + 7 owned rows -> its LAST owned row
-    assert n_row == nxt + off + row_b               # its FIRST owned row
-    assert (flags, p_flag, n_flag) == (local, prev + 8, nxt)
-    assert status == local + peer_halo.STATUS_OFFSET and x == local + off + row_b
-    assert [c[5] for c in calls] == [1, 2]          # one epoch per evaluation
+    assert [c[0] for c in calls] == ['push', 'kernel', 'push', 'kernel']
+    assert [c[9] for c in calls] == [5, 5, 9, 5]
+    for kind, p_ghost, n_ghost, flags, p_flag, n_flag, epoch, status, x, _ in calls:
+        assert p_ghost == prev + off + row_b * 8         # ghost slot + 7 owned rows -> the ghost row ABOVE them
+        assert n_ghost == nxt + off                      # the ghost row BELOW its first owned row
+        assert (flags, p_flag, n_flag) == (local, prev + 8, nxt)
+        assert status == local + peer_halo.STATUS_OFFSET and x == local + off + row_b
+    assert [c[6] for c in calls] == [1, 1, 2, 2]         # one epoch per evaluation, same for push and kernel
+    # push and kernel can be issued separately (all pushes of an evaluation first)
+    launch(ctypes.c_void_p(5), kernel=False)
+    launch(ctypes.c_void_p(5), push=False)
+    assert [c[0] for c in calls[-2:]] == ['push', 'kernel'] and [c[6] for c in calls[-2:]] == [3, 3]
     # first / last strips have one neighbour only; a missing region is refused
     g.row_begin, g.row_count = 0, 7
     first = peer_halo.PeerStripResidual(g, local, 0, nxt, 0, rows_max, n_sets)
     first.residual(0, None, None, None, ctypes.c_void_p(0))
-    assert calls[-1][0] is None and calls[-1][3] is None and calls[-1][1] == nxt + peer_halo.HEADER_BYTES + row_b
+    assert calls[-1][1] is None and calls[-1][4] is None and calls[-1][2] == nxt + peer_halo.HEADER_BYTES
     with pytest.raises(ValueError):
         peer_halo.PeerStripResidual(g, local, 0, 0, 0, rows_max, n_sets)
 
