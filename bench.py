@@ -126,27 +126,37 @@ def _use_all_host_threads(reexec=False):
         return cores
 
 
-def cpu_reference_residual(seconds_budget=12.0, nx=NX, ny=NY):
-    """reference C++-OpenMP residual through its pybind11 entry (the reference path, Python
-    overhead included), all host threads; returns (Mcells/s best-of-N, cores, kind, sample)."""
+def _cpu_residual_fn(nx, ny):
+    """the reference's C++-OpenMP residual through its pybind11 entry (oracle/_ref: the reference's
+    own sources compiled unchanged), or the oracle's C port when the reference was not built"""
     from oracle import ldc_oracle as orc
     g, X = synthetic_case(nx, ny)
     try:
         ref = orc.ref_module()
-        fn, kind = (lambda: ref.residual_function_omp(X, g)), 'reference'
+        return (lambda: ref.residual_function_omp(X, g)), 'reference'
     except Exception:
-        fn, kind = (lambda: orc.residual_function(X, g, nthreads=0)), 'port'
+        return (lambda: orc.residual_function(X, g, nthreads=0)), 'port'
+
+
+def cpu_reference_residual(seconds_budget=10.0, nx=NX, ny=NY, max_calls=200, warm=5):
+    """All host threads.  Returns (Mcells/s from the MEAN call time after `warm` warm-up calls --
+    the statistic `--impl reference` reports --, cores, kind, sample text, Mcells/s of the BEST
+    call).  Mean and best differ by ~2x at 1024^2: every call of the reference allocates its 25 MB
+    result array, and the page faults of a fresh allocation land in some calls and not in others."""
+    fn, kind = _cpu_residual_fn(nx, ny)
     cores = _use_all_host_threads()
-    fn()
+    for _ in range(warm):
+        fn()
     times, t_start = [], time.time()
-    while time.time() - t_start < seconds_budget and len(times) < 200:
+    while (time.time() - t_start < seconds_budget and len(times) < max_calls) or len(times) < 3:
         t0 = time.perf_counter()
         fn()
         times.append(time.perf_counter() - t0)
-    best = min(times)
-    sample = '%d calls of residual_function%s on %dx%d synthetic inputs, best wall time' % (
-        len(times), '_omp (c++/residual_function_omp.cpp, g++ -O2 -fopenmp)' if kind == 'reference' else ' (oracle port)', nx, ny)
-    return nx * ny / best / 1e6, cores, kind, sample, best
+    mean, best = sum(times) / len(times), min(times)
+    sample = '%d calls (after %d warm-up calls) of residual_function%s on %dx%d synthetic inputs, mean wall time' % (
+        len(times), warm, '_omp (c++/residual_function_omp.cpp, g++ -O2 -fopenmp)' if kind == 'reference'
+        else ' (oracle port)', nx, ny)
+    return nx * ny / mean / 1e6, cores, kind, sample, nx * ny / best / 1e6
 
 
 def run_reference_arm(args):
@@ -154,13 +164,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     warm, steps = max(args.warmup, 1), max(args.steps, 1)
-    from oracle import ldc_oracle as orc
-    g, X = synthetic_case(NX, NY)
-    try:
-        ref = orc.ref_module()
-        fn, kind = (lambda: ref.residual_function_omp(X, g)), 'reference'
-    except Exception:
-        fn, kind = (lambda: orc.residual_function(X, g, nthreads=0)), 'port'
+    fn, kind = _cpu_residual_fn(NX, NY)
     cores = _use_all_host_threads()
     for _ in range(warm):
         fn()
@@ -215,7 +219,8 @@ def time_to_converge(max_seconds=120.0):
     return {"grid": "%dx%d" % (NX, NY), "Re": RE, "seconds": round(sec, 3), "status": status,
             "time_steps": len(steps), "newton_iterations": wrapper.total_newton_iterations,
             "krylov_iterations": wrapper.total_linear_iterations,
-            "residual_evaluations_equivalent": wrapper.total_function_evaluations,
+            "residual_evaluations": wrapper.total_function_evaluations,
+            "fd_jacobian_launches": wrapper.total_jacobian_evaluations,
             "pseudo_time": steps[-1] if steps else 0.0}
 
 
@@ -233,7 +238,7 @@ def _time_loop(fn, n_sets, iters, warmup=3):
     return e0.elapsed_time(e1) / iters
 
 
-def named_sizes_table(peak):
+def named_sizes_table(peak, with_cpu=True):
     """residual kernel on every grid BASELINE.json names (kernel-only, CUDA events, L2-cold by
     rotating buffer sets): Mcells/s and fraction of the HBM roofline at 8*(8N-nx-ny) bytes."""
     import torch
@@ -261,6 +266,12 @@ def named_sizes_table(peak):
         rows.append({"grid": "%dx%d" % (nx, ny) + (" x%d" % batch if batch > 1 else ""), "kernel_ms": round(ms, 5),
                      "mcells_per_s": round(N * batch / ms / 1e3, 1), "gb_per_s": round(gbs, 1),
                      "frac_of_hbm_peak": round(gbs / peak, 4)})
+        if with_cpu:
+            # the reference evaluates one cavity per call (no batch): 512 x 64^2 = 512 calls of 64^2
+            v, cores, kind, _, best = cpu_reference_residual(2.0 if N < 4e6 else 4.0, nx, ny, max_calls=100, warm=2)
+            rows[-1]["cpu_mcells_per_s"] = round(v, 1)
+            rows[-1]["cpu_best_call_mcells_per_s"] = round(best, 1)
+            rows[-1]["cpu"] = "%s, %d threads" % (kind, cores)
         del Xs, Fs, Us, Vs, Xd
         torch.cuda.empty_cache()
     return rows
@@ -308,34 +319,291 @@ def spmv_table(peak, n=1024):
                                 "frac_of_hbm_peak": round(fd_bytes / ms_fd / 1e6 / peak, 4)}}
 
 
-def cpu_solve_sample(budget=25.0):
-    """Bounded sample of the reference path for the solve (PETSc-equivalent restatement, PETSc is
-    not installable): one FD Jacobian + ILU(0) + a few GMRES(30) iterations of the FIRST Newton
-    iteration at 1024^2 Re=1000.  Returns per-unit costs; the full run would need
-    ~(krylov its) x (s per Krylov it), hours."""
+def cpu_solve_lower_bound(gpu_seconds, factor=60.0, min_budget=45.0, max_budget=150.0, nx=None, ny=None):
+    """The CPU path's time-to-converge at 1024^2 Re=1000, timed in this run on this box's host
+    cores under a DEADLINE of `factor` x the GPU's whole time-to-converge.  The reference's solve
+    is PETSc SNES (newtonls/basic) + coloured FD Jacobian + GMRES(30)/ILU(0), ksp_rtol 1e-5
+    (petsc_solver_wrapper.py:112-145) inside time_stepper.run_simulation; PETSc / petsc4py are
+    not installable here, so the CPU arm is the oracle's restatement of exactly that configuration
+    (kind "port"; OpenMP over all host threads where PETSc's sequential objects would use one).
+    It runs the SAME recipe the GPU ran (run_solver.py:42-67) from the same start until it is
+    steady or the deadline passes.  Converged in time: a measured speed-up.  Deadline passed: the
+    CPU path's time-to-converge is MORE than the time spent, so speed-up > spent / GPU seconds --
+    a measured lower bound, not an extrapolation; `progress` says how far it got."""
     from oracle import ldc_oracle as orc
     from lid_driven_cavity_problem_b200.staggered_grid import Graph
-    g = Graph(1.0, 1.0, NX, NY, 1e-2, 1.0, 1.0, RE)
-    X = orc.create_X(g.ns_x_mesh.phi, g.ns_y_mesh.phi, g.pressure_mesh.phi, g)
+    nx, ny = nx or NX, ny or NY
+    budget = min(max(factor * gpu_seconds, min_budget), max_budget)
+    t_start = time.time()
+    left = lambda: budget - (time.time() - t_start)   # noqa: E731
+    g = Graph(1.0, 1.0, nx, ny, 1e-2, 1.0, 1.0, RE)
+    mask = orc.jacobian_mask_arrays(nx, ny, 3)
+    U, V, P = (np.array(a, dtype=np.float64) for a in (g.ns_x_mesh.phi, g.ns_y_mesh.phi, g.pressure_mesh.phi))
+    dt, t_it = 1e-2, None
+    steps = retries = newton = gm = 0
+    t_jac = t_ilu = t_gm = 0.0
+    where, finished = "", False
+    while not finished and left() > 0:
+        g.dt = dt
+        g.ns_x_mesh.phi_old, g.ns_y_mesh.phi_old, g.pressure_mesh.phi_old = U, V, P
+        X = orc.create_X(U, V, P, g)
+        F = orc.residual_function(X, g, nthreads=0)
+        fnorm = float(np.linalg.norm(F))
+        ttol, reason = fnorm * 1e-4, (2 if fnorm < 1e-4 else 0)
+        it = 0
+        while reason == 0 and it < 50:
+            where = "time step %d (dt=%.3g), Newton iteration %d" % (steps + 1, dt, it + 1)
+            if left() <= 0:
+                break
+            t0 = time.time()
+            J = orc.fd_jacobian(X, g, F0=F, mask=mask, nthreads=0)
+            t_jac += time.time() - t0
+            t0 = time.time()
+            lu, diag, _, _ = orc.ilu0(mask, J)
+            t_ilu += time.time() - t0
+            if t_it is None:     # cost of one GMRES iteration, from a short probe
+                t0 = time.time()
+                _, _, k0, _ = orc.gmres_ilu0(mask, J, lu, diag, F, max_it=6, nthreads=0)
+                t_it = (time.time() - t0) / max(k0, 1)
+            cap = int(min(10000, max(30, left() / t_it)))      # ONE uninterrupted GMRES run sized to the deadline
+            t0 = time.time()
+            y, kreason, kits, rn = orc.gmres_ilu0(mask, J, lu, diag, F, max_it=cap, nthreads=0)
+            t_gm += time.time() - t0
+            gm += kits
+            if kreason <= 0:
+                if cap < 10000:   # stopped by the deadline, not by PETSc's own iteration limit
+                    rel = rn / float(np.linalg.norm(orc.ilu0_solve(mask, lu, diag, F)))
+                    where += ", linear solve NOT converged after %d GMRES iterations (preconditioned relative " \
+                             "residual %.2e, ksp_rtol 1e-5)" % (kits, rel)
+                    reason = None
+                else:
+                    reason = -3
+                break
+            X = X - y
+            F = orc.residual_function(X, g, nthreads=0)
+            it += 1
+            newton += 1
+            fnorm, ynorm, xnorm = (float(np.linalg.norm(v)) for v in (F, y, X))
+            if fnorm != fnorm: reason = -4
+            elif fnorm < 1e-4: reason = 2
+            elif fnorm <= ttol: reason = 3
+            elif ynorm < 1e-4 * xnorm: reason = 4
+            elif it >= 50: reason = -5
+        if reason is None or reason == 0:
+            break                                   # deadline
+        if reason < 0:                              # diverged: the stepper halves dt and retries
+            retries += 1
+            dt /= 2.0
+            continue
+        Un, Vn, Pn = orc.recover_X(X, g)
+        steps += 1
+        du = float(np.abs(Un - U).max()) / RE
+        U, V, P = Un, Vn, Pn
+        if du < 1e-6:
+            finished = True
+        dt *= 1.2
+    spent = time.time() - t_start
+    out = {"kind": "port (oracle restatement of the reference's PETSc configuration: SNES newtonls/basic, "
+                   "21-colour FD Jacobian, left-preconditioned GMRES(30) + ILU(0), ksp_rtol 1e-5, inside the "
+                   "reference's time stepper; PETSc/petsc4py are not installable)",
+           "grid": "%dx%d" % (nx, ny), "cores": os.cpu_count(), "deadline_s": round(budget, 1),
+           "seconds_spent": round(spent, 2), "converged": finished, "time_steps_done": steps, "dt_halvings": retries,
+           "newton_iterations_done": newton, "gmres_iterations_done": gm,
+           "fd_jacobian_s": round(t_jac, 2), "ilu0_s": round(t_ilu, 2), "gmres_s": round(t_gm, 2),
+           "s_per_gmres_iteration": round(t_gm / max(gm, 1), 4)}
+    if finished:
+        out["speedup"] = round(spent / gpu_seconds, 1)
+    else:
+        out["progress_at_deadline"] = where
+        out["cpu_time_to_converge_s_greater_than"] = round(spent, 2)
+        out["speedup_greater_than"] = round(spent / gpu_seconds, 1)
+    return out
+
+
+def small_grid_full_runs():
+    """Both arms run to the SAME steady state on a grid the CPU path finishes in seconds:
+    64x64 Re=400, reference recipe, complete runs, wall clock (setup included on both sides)."""
+    import torch
+    from oracle import ldc_oracle as orc
+    from lid_driven_cavity_problem_b200.nonlinear_solver import cuda_solver_wrapper
+    from lid_driven_cavity_problem_b200.staggered_grid import Graph
+    from lid_driven_cavity_problem_b200.time_stepper import run_simulation
+    n, re = 64, 400.0
+    w = cuda_solver_wrapper.CudaSolverWrapper(None)
+    run_simulation(Graph(1.0, 1.0, n, n, 1e-2, 1.0, 1.0, re), None, w.solve, max_steps=1)   # warm-up: module load
+    w.close()
+    w = cuda_solver_wrapper.CudaSolverWrapper(None)
+    torch.cuda.synchronize()
     t0 = time.time()
-    mask = orc.jacobian_mask_arrays(NX, NY, 3)
-    t_mask = time.time() - t0
+    out = run_simulation(Graph(1.0, 1.0, n, n, 1e-2, 1.0, 1.0, re), None, w.solve)
+    U_gpu = np.array(out.ns_x_mesh.phi)
+    t_gpu = time.time() - t0
+    w.close()
     t0 = time.time()
-    F = orc.residual_function(X, g, nthreads=0)
-    J = orc.fd_jacobian(X, g, F0=F, mask=mask, nthreads=0)
-    t_jac = time.time() - t0
+    ref, hist = orc.run_simulation(Graph(1.0, 1.0, n, n, 1e-2, 1.0, 1.0, re), None, linear='gmres_ilu0', nthreads=0)
+    t_cpu = time.time() - t0
+    return {"grid": "%dx%d" % (n, n), "Re": re, "gpu_seconds": round(t_gpu, 3), "cpu_seconds": round(t_cpu, 3),
+            "cpu_kind": "port (oracle: SNES newtonls + coloured FD + GMRES(30)/ILU(0)), %d threads" % (os.cpu_count() or 1),
+            "speedup": round(t_cpu / t_gpu, 1), "cpu_time_steps": len(hist),
+            "max_dU_over_bc_between_the_two_steady_states": float(np.abs(U_gpu - ref.ns_x_mesh.phi).max() / re)}
+
+
+def _max_over_ranks(values, world):
+    """element-wise max over ranks of a short list of floats (device all-reduce)"""
+    if world == 1:
+        return [float(v) for v in values]
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64, device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t.tolist()]
+
+
+class _Stop(Exception):
+    pass
+
+
+def strips_config5(comm, rank, world, peak, n=4096, max_seconds=150.0):
+    """BASELINE config 5: ONE 4096x4096 Re=1000 cavity, STRONG scaling over `world` row strips
+    (rows/GPU = 4096/world), reference recipe (run_solver.py:42-67: dt0=1e-2, P=U=V=1, steady
+    test max|U-U_old|/bc < 1e-6).  Reports (a) the distributed building blocks exactly as the
+    solve issues them -- residual + norm, outer SpMV, Gram-Schmidt dots, one multigrid cycle; halo
+    exchanges and all-reduces included; max over ranks -- and (b) the wall time of the whole steady
+    solve.  world = 1 is the single-GPU number the others are compared with (that solver may run
+    its preconditioner cycle in fp32, the distributed one runs it in fp64)."""
+    import torch
+    import torch.distributed as dist
+    from lid_driven_cavity_problem_b200 import _native
+    from lid_driven_cavity_problem_b200.strip_solver import CudaStripSolver
+    lib = _native.lib()
+    solver = CudaStripSolver(n, n, 1e-2, 1.0, 1.0, RE, comm=comm, rank=rank, world=world)
+    out = {"grid": "%dx%d" % (n, n), "Re": RE, "gpus": world, "rows_per_gpu": solver.row_count, "scaling": "strong"}
+    try:
+        solver.set_uniform_state()
+        ms = (ctypes.c_double * 4)()
+        _native.check(lib.ldc_solver_time_ops(solver._handle, 10, ms, _native.current_stream()), 'ldc_solver_time_ops')
+        ms = _max_over_ranks(list(ms), world)
+        N = n * n
+        alg = [8 * (8 * N - 2 * n), (26 * 8 + 48) * N, 16 * 24 * N]   # residual, compact SpMV, 15 dots + w
+        names = ["residual_and_norm", "spmv_outer", "gram_schmidt_15_dots"]
+        out["kernels"] = {nm: {"ms": round(m, 5), "gb_per_s_all_gpus": round(b / m / 1e6, 1),
+                               "frac_of_hbm_peak_x_gpus": round(b / m / 1e6 / (peak * world), 4)}
+                          for nm, m, b in zip(names, ms[:3], alg)}
+        out["kernels"]["multigrid_cycle"] = {"ms": round(ms[3], 5)}
+        solver.set_uniform_state()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.time()
+
+        def on_step(t, dt, rep, du):
+            # every rank must take the same decision: agree on the elapsed time
+            if _max_over_ranks([time.time() - t0], world)[0] > max_seconds:
+                raise _Stop()
+        status = "converged (reference steady test: max|U-U_old|/bc < 1e-6)"
+        try:
+            solver.run(on_step=on_step)
+        except _Stop:
+            status = "stopped after %.0f s" % max_seconds
+        torch.cuda.synchronize()
+        sec = _max_over_ranks([time.time() - t0], world)[0]
+        out.update({"seconds": round(sec, 3), "status": status, "time_steps": solver.steps,
+                    "dt_halvings": solver.retries, "newton_iterations": solver.newton_iterations,
+                    "krylov_iterations": solver.krylov_iterations})
+    finally:
+        solver.close()
+        torch.cuda.empty_cache()
+    return out
+
+
+def strip_solve_parity(comm, rank, world, n=256, steps=3):
+    """N > 1: the distributed row-strip solve against the single-GPU solve of the same cavity
+    (n x n, Re=1000, `steps` pseudo-time steps, default options), compared on rank 0 after
+    gathering the strips.  The distributed multigrid is algorithmically the single-GPU one, so
+    the two agree to summation-order noise."""
+    import torch
+    from lid_driven_cavity_problem_b200.strip_solver import CudaStripSolver
+    opts = dict(pc_fp32=0)     # the distributed cycle runs in fp64; compare like with like
+    dist_solver = CudaStripSolver(n, n, 1e-2, 1.0, 1.0, RE, comm=comm, rank=rank, world=world, **opts)
+    dist_solver.set_uniform_state()
+    dist_solver.run(max_steps=steps)
+    X = dist_solver.gather_state()
+    its = dist_solver.krylov_iterations
+    dist_solver.close()
+    out = None
+    if rank == 0:
+        one = CudaStripSolver(n, n, 1e-2, 1.0, 1.0, RE, **opts)
+        one.set_uniform_state()
+        one.run(max_steps=steps)
+        X1 = one.get_state()
+        d = (X - X1).abs()
+        scale_u = float(X1[1::3].abs().max())
+        P, P1 = X[0::3], X1[0::3]
+        dP = ((P - P.mean()) - (P1 - P1.mean())).abs().max()
+        out = {"grid": "%dx%d" % (n, n), "time_steps": steps,
+               "max_dU_rel": float(d[1::3].max()) / scale_u, "max_dV_rel": float(d[2::3].max()) / scale_u,
+               "max_dP_rel": float(dP) / float((P1 - P1.mean()).abs().max()),
+               "krylov_iterations": [int(its), int(one.krylov_iterations)]}
+        out["agrees_to_1e-8"] = bool(max(out["max_dU_rel"], out["max_dV_rel"], out["max_dP_rel"]) < 1e-8)
+        one.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def ensemble_config4(rank, world, count=512, n=64, max_sweeps=None):
+    """BASELINE config 4: `count` independent n x n cavities, Re log-spaced 100..10000, dealt
+    round-robin to the ranks (every GPU gets the same mix of easy and hard cavities), each rank
+    one batched device solver, NO data-path collective; every cavity runs the reference recipe
+    to its own steady state.  Time = max over ranks (barrier on both sides)."""
+    import torch
+    import torch.distributed as dist
+    from lid_driven_cavity_problem_b200.ensemble import run_ensemble, STEADY, FAILED
+    from lid_driven_cavity_problem_b200.staggered_grid import Graph
+    res = 100.0 * (10000.0 / 100.0) ** (np.arange(count) / max(count - 1, 1))
+    graphs = [Graph(1.0, 1.0, n, n, 1e-2, 1.0, 1.0, float(r)) for r in res]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.time()
-    lu, diag, _, _ = orc.ilu0(mask, J)
-    t_ilu = time.time() - t0
-    its = 8
-    t0 = time.time()
-    _, reason, kits, rn = orc.gmres_ilu0(mask, J, lu, diag, F, max_it=its, nthreads=0)
-    t_gm = (time.time() - t0) / max(kits, 1)
-    return {"kind": "port (PETSc-equivalent restatement; PETSc/petsc4py not installable)",
-            "cores": os.cpu_count(), "mask_s": round(t_mask, 3), "fd_jacobian_s": round(t_jac, 3),
-            "ilu0_factor_s": round(t_ilu, 3), "s_per_gmres_iteration": round(t_gm, 4),
-            "sample": "1024x1024 Re=1000, first Newton iteration: mask + 21-colour FD Jacobian + ILU(0) "
-                      "+ %d GMRES(30) iterations" % kits}
+    summ, _ = run_ensemble(graphs, max_steps=max_sweeps, distributed=world > 1, interleave=True)
+    torch.cuda.synchronize()
+    sec = _max_over_ranks([time.time() - t0], world)[0]
+    st = np.array([d['status'] for d in summ])
+    cells = count * n * n
+    return {"cavities": count, "grid": "%dx%d" % (n, n), "Re": [100.0, 10000.0], "gpus": world,
+            "cavities_per_gpu": (count + world - 1) // world, "scaling": "strong", "seconds": round(sec, 3),
+            "steady": int((st == STEADY).sum()), "failed": int((st == FAILED).sum()),
+            "time_steps_total": int(sum(d['steps'] for d in summ)),
+            "dt_halvings_total": int(sum(d['retries'] for d in summ)),
+            "newton_total": int(sum(d['newton'] for d in summ)), "krylov_total": int(sum(d['krylov'] for d in summ)),
+            "cavities_per_s": round(count / sec, 2),
+            "mcell_time_steps_per_s": round(sum(d['steps'] for d in summ) * n * n / sec / 1e6, 3)}
+
+
+def residual_parity_vs_single_gpu(lib, grid, rank, world, X_strip, U_strip, V_strip, F_strip, nx, ny_local):
+    """N > 1: every rank assembles the WHOLE 1024 x (1024*N) cavity (all-gather of the strips'
+    inputs), evaluates it alone with the plain single-GPU kernel and compares its own rows with
+    what the multi-GPU step produced: bit-identical or not, min over ranks."""
+    import torch
+    import torch.distributed as dist
+    from lid_driven_cavity_problem_b200 import _native
+
+    def gather(t):
+        full = torch.empty(t.numel() * world, dtype=t.dtype, device='cuda')
+        dist.all_gather_into_tensor(full, t.contiguous())
+        return full
+    Xf, Uf, Vf = gather(X_strip), gather(U_strip), gather(V_strip[:nx * ny_local])
+    Ff = torch.empty_like(Xf)
+    full = _native.LdcGrid()
+    ctypes.memmove(ctypes.byref(full), ctypes.byref(grid), ctypes.sizeof(grid))
+    full.row_begin, full.row_count = 0, grid.ny
+    _native.check(lib.ldc_residual(full, _native.ptr(Xf), _native.ptr(Uf), _native.ptr(Vf), _native.ptr(Ff),
+                                   None, None, 0, _native.current_stream()), 'ldc_residual')
+    mine = Ff[3 * nx * ny_local * rank: 3 * nx * ny_local * (rank + 1)]
+    same = torch.tensor([1.0 if torch.equal(mine, F_strip) else 0.0], dtype=torch.float64, device='cuda')
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    return bool(same.item() == 1.0)
+
 
 
 def main():
@@ -347,6 +615,8 @@ def main():
     ap.add_argument('--no-solve', action='store_true', help='skip the time-to-converge run')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline legs')
     ap.add_argument('--no-tables', action='store_true', help='skip the per-size / per-kernel tables')
+    ap.add_argument('--no-strips', action='store_true', help='skip the 4096^2 row-strip solve (config 5)')
+    ap.add_argument('--no-ensemble', action='store_true', help='skip the 512 x 64^2 Reynolds ensemble (config 4)')
     args = ap.parse_args()
     if args.impl == 'reference':
         if int(os.environ.get('RANK', '0')) == 0:
@@ -473,22 +743,39 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_region(step_fn):
+        """EXACTLY `steps` steps between barrier + synchronize on both sides, CUDA events on the
+        launch stream, max over ranks; returns (ms of the region, host enqueue us per step)"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        t_host = time.perf_counter()
+        for k in range(steps):
+            step_fn(k % n_sets)
+        enqueue_us = (time.perf_counter() - t_host) / steps * 1e6
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, enqueue_us
+
     for k in range(warm):
         step(k % n_sets)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    t_host = time.perf_counter()
-    for k in range(steps):
-        step(k % n_sets)
-    host_us = (time.perf_counter() - t_host) / steps * 1e6   # enqueue cost per step on this rank
-    ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
+    # A region of K steps lasts K x 14 us -- 0.3 ms at the driver's K = 20 -- so one region is at
+    # the mercy of a single scheduling hiccup.  The region is therefore measured REGIONS times
+    # (each one exactly K steps, bracketed as the contract says) and the MEDIAN region is
+    # reported; all of them are listed under `regions_ms_per_step`.
+    REGIONS = 7
+    regions = [timed_region(step) for _ in range(REGIONS)]
+    order = sorted(range(REGIONS), key=lambda i: regions[i][0])
+    ms_total, host_us = regions[order[REGIONS // 2]]
     # keep the GPU busy long enough for the clock sampler to see it under load
     if rank == 0:
         t_end = time.time() + 0.6
@@ -498,10 +785,6 @@ def main():
             k += 1
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
     ms_step = ms_total / steps
     value = N * world / (ms_step * 1e-3) / 1e6
     nccl_ms = None
@@ -511,15 +794,7 @@ def main():
         # the same step with the NCCL halo exchange in front of the kernel, for comparison
         for k in range(warm):
             step_nccl(k % n_sets)
-        barrier()
-        ev0.record()
-        for k in range(steps):
-            step_nccl(k % n_sets)
-        ev1.record()
-        barrier()
-        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        nccl_ms = float(t.item()) / steps
+        nccl_ms = sorted(timed_region(step_nccl)[0] for _ in range(3))[1] / steps
         # both paths must give the same bits on every rank
         step(0)
         F_peer = Fs[0].clone()
@@ -530,14 +805,17 @@ def main():
         halo_identical = bool(same.item() == 1.0) and not peer_strip.status()
 
     # ---- kernel-only roofline (single launch stream, CUDA events, no halo exchange)
-    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    ev2.record()
-    for k in range(steps):
-        kernel_only(k % n_sets)
-    ev3.record()
-    torch.cuda.synchronize()
-    kern_ms = ev2.elapsed_time(ev3) / steps
+    kern_regions = []
+    for _ in range(REGIONS):
+        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev2.record()
+        for k in range(steps):
+            kernel_only(k % n_sets)
+        ev3.record()
+        torch.cuda.synchronize()
+        kern_regions.append(ev2.elapsed_time(ev3) / steps)
+    kern_ms = sorted(kern_regions)[REGIONS // 2]
     peak, peak_kind = hbm_peak()
     achieved = res_bytes / (kern_ms * 1e-3) / 1e9
 
@@ -559,6 +837,33 @@ def main():
     n_unknowns = 3 * NX * NY
     h2d = 8 * (n_unknowns + (NX - 1) * NY + NX * (NY - 1))
     d2h = 8 * n_unknowns
+
+    # ---- the sharded BASELINE configurations (every rank takes part)
+    peak, peak_kind = hbm_peak()
+    extras = {}
+    if world > 1:
+        par = {}
+        try:
+            step(0)
+            par["residual_strips_bit_identical_to_single_gpu_evaluation"] = residual_parity_vs_single_gpu(
+                lib, grid, rank, world, Xbuf[0][row:row * (ny_local + 1)], Ud[0], Vd[0], Fs[0], nx, ny_local)
+            if not args.no_strips:
+                par["strip_solve_vs_single_gpu"] = strip_solve_parity(comm, rank, world)
+        except Exception as e:   # never lose the headline line
+            par["error"] = repr(e)
+        extras["multi_gpu_parity"] = par
+    del Xbuf, Fs, Ud, Vd
+    torch.cuda.empty_cache()
+    if not args.no_strips:
+        try:
+            extras["strips_4096"] = strips_config5(comm, rank, world, peak)
+        except Exception as e:
+            extras["strips_4096"] = {"error": repr(e)}
+    if not args.no_ensemble:
+        try:
+            extras["ensemble_512x64"] = ensemble_config4(rank, world)
+        except Exception as e:
+            extras["ensemble_512x64"] = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -600,12 +905,14 @@ def main():
         line["halo"] = {"fused_peer_ms_per_step": ms_step, "nccl_sendrecv_then_kernel_ms_per_step": nccl_ms,
                         "kernel_only_ms": kern_ms, "bit_identical_to_nccl_path": halo_identical,
                         "host_enqueue_us_per_step": round(host_us, 2)}
+    line.update(extras)
     if not args.no_cpu:
         v, cores, kind, sample, best = cpu_reference_residual()
-        line["cpu_baseline"] = {"value": v, "unit": "Mcells/s", "cores": cores, "kind": kind, "sample": sample}
+        line["cpu_baseline"] = {"value": v, "unit": "Mcells/s", "cores": cores, "kind": kind, "sample": sample,
+                                "best_call_value": best}
     if world == 1 and not args.no_tables:
         try:
-            line["named_sizes"] = named_sizes_table(peak)
+            line["named_sizes"] = named_sizes_table(peak, with_cpu=not args.no_cpu)
             line["other_kernels"] = spmv_table(peak)
         except Exception as e:
             line["named_sizes"] = {"error": repr(e)}
@@ -613,7 +920,9 @@ def main():
         try:
             line["time_to_converge"] = time_to_converge()
             if not args.no_cpu:
-                line["time_to_converge"]["cpu_reference_sample"] = cpu_solve_sample()
+                line["time_to_converge"]["cpu_path_same_run"] = cpu_solve_lower_bound(
+                    line["time_to_converge"]["seconds"])
+                line["time_to_converge"]["complete_runs_small_grid"] = small_grid_full_runs()
         except Exception as e:  # the solve is an extra; never lose the headline line
             line["time_to_converge"] = {"error": repr(e)}
     print(json.dumps(line))

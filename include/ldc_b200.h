@@ -72,6 +72,19 @@ LDC_API int ldc_residual(const ldc_grid *g, const double *X_dev, const double *U
                  const double *V_old_dev, double *F_dev, double *norm2_dev, double *work_dev,
                  int32_t variant, void *stream);
 
+/* ---- the same plug point with HOST buffers (what the reference's callers hold: PETSc's callback
+ * and scipy's fsolve pass numpy arrays, petsc_solver_wrapper.py:42-48, scipy_solver_wrapper.py:35;
+ * c++/residual_function.cpp:10-43 takes and returns host arrays).  X_host[3*nx*ny],
+ * U_old_host[(nx-1)*ny], V_old_host[nx*(ny-1)] are read, F_host[3*nx*ny] is written; any
+ * pageable memory.  The call is a copy pipeline over row blocks: multi-threaded staging into
+ * pinned memory, H2D, the strip form of ldc_residual per block, D2H and copy-out overlap, with
+ * both PCIe directions busy at once.  Synchronous (F_host is complete on return); buffers,
+ * streams and copy threads are created once per process; calls are serialised.  batch must be
+ * 1, dt_dev / bc_dev NULL.  LDC_HOST_COPY_THREADS overrides the copy-thread count (default:
+ * min(8, cores / LOCAL_WORLD_SIZE)). */
+LDC_API int ldc_residual_host(const ldc_grid *g, const double *X_host, const double *U_old_host,
+                      const double *V_old_host, double *F_host, int32_t variant);
+
 /* ---- residual of one row strip per GPU without a collective (the reference has no
  * multi-rank path).  Buffers use the strip layout above: [ghost row | row_count owned rows | ghost
  * row], and every strip's buffer is mapped into its neighbours' address space (CUDA IPC / peer
@@ -211,12 +224,14 @@ LDC_API void ldc_solver_default_options(ldc_solver_options *opt);
 /* result of one Newton solve, per instance; reason codes are PETSc's SNESConvergedReason as
  * tabulated in petsc_solver_wrapper.py:12-31 (2,3,4 converged; -2..-5 diverged). */
 typedef struct ldc_newton_report {
-    int32_t reason;
-    int32_t iterations;
-    int32_t function_evaluations;
-    int32_t linear_iterations;
-    int32_t ksp_reason;
-    int32_t reserved;
+    int32_t reason;                /* SNESConvergedReason codes of petsc_solver_wrapper.py:12-31, plus -9 */
+    int32_t iterations;            /* Newton iterations */
+    int32_t function_evaluations;  /* residual kernel evaluations actually made (1 + iterations); what
+                                      snes_max_funcs is compared with.  PETSc would also count the 21
+                                      coloured evaluations of each FD Jacobian, which here are ONE launch: */
+    int32_t linear_iterations;     /* Krylov iterations, summed over the Newton iterations */
+    int32_t ksp_reason;            /* KSPConvergedReason-like code of the last linear solve */
+    int32_t jacobian_evaluations;  /* FD Jacobian launches (all colours at once) */
     double fnorm0, fnorm, xnorm, ynorm;
 } ldc_newton_report;
 
@@ -235,19 +250,40 @@ LDC_API int ldc_solver_get_state(ldc_solver *s, double *X_dev, void *stream);
  * Krylov basis, Jacobian rows); with a transport attached, halo rows of the state and of every
  * SpMV input are exchanged with the neighbouring strips and every norm / Gram-Schmidt coefficient
  * is all-reduced, so all ranks take identical decisions.  The preconditioner is block-Jacobi
- * over strips (each strip runs its own multigrid cycle). */
+ * over strips (each strip runs its own multigrid cycle).  COLLECTIVE: the call all-reduces the
+ * strip height, the number of multigrid levels and the replication level and fails on EVERY rank
+ * unless they are identical everywhere (equal strips: ny divisible by the number of ranks) --
+ * ranks with different hierarchies would issue different sequences of collectives and hang. */
 LDC_API int ldc_solver_set_comm(ldc_solver *s, const ldc_comm_ops *ops);
 /* out3 = {Krylov iterations executed in lock step, sum over cavities of their own Krylov
  * iterations, Newton iterations (Jacobian builds) executed} since creation */
 LDC_API int ldc_solver_counters(ldc_solver *s, int64_t *out3);
+/* keep != 0: instances whose Newton solve diverged keep their last iterate (what the reference
+ * returns under options.IGNORE_DIVERGED, petsc_solver_wrapper.py:90-103) instead of being rolled
+ * back to the state they entered ldc_solver_step with (the default: the time stepper retries
+ * from the old state, time_stepper.py:23-32).  du_inf is computed on whatever state is kept. */
+LDC_API int ldc_solver_set_keep_diverged(ldc_solver *s, int32_t keep);
 /* number of multigrid levels the solver built */
 LDC_API int ldc_solver_num_levels(ldc_solver *s);
+/* Shape of the hierarchy ldc_solver_create would build for the cavity / row strip `g`: number of
+ * levels and the first level that is replicated on every rank (-1: none).  Host arithmetic only
+ * (no device needed).  All ranks of a distributed solve must obtain the same answer;
+ * ldc_solver_set_comm verifies that collectively and refuses the partition otherwise. */
+LDC_API int ldc_solver_plan_levels(const ldc_grid *g, const ldc_solver_options *opt, int32_t *levels_out,
+                           int32_t *replicated_from_out);
 /* Building block exposed for the parity tests: assemble the FD Jacobian (and its multigrid
  * hierarchy) at the current state and solve J y = rhs with the preconditioned GMRES.
  * Host outputs are per instance.  Synchronises the stream. */
 LDC_API int ldc_solver_linear_solve(ldc_solver *s, const double *rhs_dev, double *y_dev,
                                     int32_t *its_host, int32_t *reason_host, double *relres_host,
                                     void *stream);
+/* Measurement hook (bench.py, row-strip table): average milliseconds of the solver's building
+ * blocks on its own data, issued exactly as the Newton / Krylov loops issue them (halo exchanges
+ * and all-reduces of a distributed solver included), CUDA events on the solver's stream:
+ * ms_out4 = { residual + norm, outer SpMV w = J v, Gram-Schmidt dots against 15 basis vectors
+ * (+ all-reduce), one preconditioner application }.  Rebuilds the Jacobian hierarchy at the
+ * current state first.  COLLECTIVE for a distributed solver.  Synchronises the stream. */
+LDC_API int ldc_solver_time_ops(ldc_solver *s, int32_t iters, double *ms_out4, void *stream);
 /* One pseudo-time step for every ACTIVE instance: X_old <- X, Newton solve, X <- solution.
  * active_host[batch] (NULL = all) selects instances; diverged instances keep X = X_old.
  * reports_host[batch] is filled.  Synchronises the stream before returning.

@@ -42,7 +42,7 @@ class LdcSolverOptions(ctypes.Structure):
 class LdcNewtonReport(ctypes.Structure):
     _fields_ = [('reason', ctypes.c_int32), ('iterations', ctypes.c_int32),
                 ('function_evaluations', ctypes.c_int32), ('linear_iterations', ctypes.c_int32),
-                ('ksp_reason', ctypes.c_int32), ('reserved', ctypes.c_int32),
+                ('ksp_reason', ctypes.c_int32), ('jacobian_evaluations', ctypes.c_int32),
                 ('fnorm0', ctypes.c_double), ('fnorm', ctypes.c_double),
                 ('xnorm', ctypes.c_double), ('ynorm', ctypes.c_double)]
 
@@ -66,6 +66,7 @@ SYMBOLS = {
     'ldc_device_info': (ctypes.c_int, [c_int32_p, c_int32_p, c_int32_p, ctypes.POINTER(_i64)]),
     'ldc_residual_work_doubles': (_i64, [_grid_p]),
     'ldc_residual': (ctypes.c_int, [_grid_p, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    'ldc_residual_host': (ctypes.c_int, [_grid_p, _vp, _vp, _vp, _vp, _i32]),
     'ldc_residual_peer_push': (ctypes.c_int, [_grid_p, ctypes.POINTER(LdcPeerHalo), _vp, _vp]),
     'ldc_residual_peer': (ctypes.c_int, [_grid_p, ctypes.POINTER(LdcPeerHalo), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'ldc_peer_ctx_create': (ctypes.c_int, [_i32, ctypes.POINTER(_vp)]),
@@ -90,7 +91,10 @@ SYMBOLS = {
     'ldc_solver_get_state': (ctypes.c_int, [_vp, _vp, _vp]),
     'ldc_solver_set_comm': (ctypes.c_int, [_vp, _vp]),
     'ldc_solver_num_levels': (ctypes.c_int, [_vp]),
+    'ldc_solver_set_keep_diverged': (ctypes.c_int, [_vp, _i32]),
+    'ldc_solver_plan_levels': (ctypes.c_int, [_grid_p, ctypes.POINTER(LdcSolverOptions), c_int32_p, c_int32_p]),
     'ldc_solver_counters': (ctypes.c_int, [_vp, ctypes.POINTER(_i64)]),
+    'ldc_solver_time_ops': (ctypes.c_int, [_vp, _i32, c_double_p, _vp]),
     'ldc_solver_linear_solve': (ctypes.c_int, [_vp, _vp, _vp, c_int32_p, c_int32_p, c_double_p, _vp]),
     'ldc_solver_step': (ctypes.c_int, [_vp, c_int32_p, ctypes.POINTER(LdcNewtonReport), c_double_p, _vp]),
 }

@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ['common.cu', 'residual.cu', 'pack.cu', 'jacobian.cu', 'spmv.cu', 'vector_ops.cu',
-           'precond.cu', 'solver.cu']
+           'precond.cu', 'solver.cu', 'host_pipeline.cu']
 LIB = os.path.join(HERE, 'libldc_b200.so')
 COMM_LIB = os.path.join(HERE, 'libldc_b200_comm.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')

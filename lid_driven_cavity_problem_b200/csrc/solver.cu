@@ -169,7 +169,8 @@ struct ldc_solver {
     cudaEvent_t ev_in;
     // row-strip decomposition
     bool strip, ghost_lo, ghost_hi, has_comm;
-    bool mixed;   // multigrid cycle in fp32 (non-distributed solvers)
+    bool keep_diverged;   // ldc_solver_set_keep_diverged: no roll-back of diverged instances
+    bool mixed;   // multigrid cycle in fp32
     ldc_comm_ops comm;
     int v_rows;
     double *X_alloc, *xpad_alloc, *xpad;
@@ -316,7 +317,8 @@ extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *op
     s->ghost_lo = g->row_begin > 0;
     s->ghost_hi = g->row_begin + g->row_count < g->ny;
     s->has_comm = false;
-    s->mixed = (o.pc_fp32 != 0) && !s->strip && o.pc_type != LDC_PC_NONE;
+    s->keep_diverged = false;
+    s->mixed = (o.pc_fp32 != 0) && o.pc_type != LDC_PC_NONE;   // strips: revisited once the levels are planned
     memset(&s->comm, 0, sizeof(s->comm));
     s->v_rows = (g->row_begin + g->row_count < g->ny ? g->row_count : g->ny - 1 - g->row_begin);
     if (s->v_rows < 0) s->v_rows = 0;
@@ -355,6 +357,16 @@ extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *op
     // the single-GPU hierarchy.
     int nlev = 1, l_rep = -1;
     plan_levels(g, o, &nlev, &l_rep);
+    if (s->strip && s->mixed) {
+        // fp32 vectors of a distributed level travel through the double-typed transport: a halo
+        // row of 3*nx floats as 3*nx/2 doubles, a slice of a replicated level likewise.  Needs even
+        // counts (true for every grid that can be coarsened at all); otherwise the cycle stays fp64.
+        for (int l = 0; l < nlev; ++l) {
+            const long nxl = g->nx >> l;
+            const bool rep = l_rep >= 0 && l >= l_rep;
+            if ((!rep || l == l_rep) && nxl % 2 != 0) s->mixed = false;   // also keeps the rows 8-byte aligned
+        }
+    }
     s->levels.resize(nlev);
     for (int l = 0; l < nlev && rc == LDC_OK; ++l) {
         MgLevel &L = s->levels[l];
@@ -405,9 +417,18 @@ extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *op
         if (s->mixed) {
             A(s->dalloc(&L.Jf, (size_t)B * 26 * L.N));
             A(s->dalloc(&L.diagf, (size_t)B * L.n));
-            A(s->dalloc(&L.xf, (size_t)B * L.n));
-            A(s->dalloc(&L.bf, (size_t)B * L.n));
-            A(s->dalloc(&L.rf, (size_t)B * L.n));
+            auto padded_f = [&](float **p) {   // like `padded`: a spare (halo) row on both sides
+                float *q = nullptr;
+                int r2 = s->dalloc(&q, (size_t)B * L.n + 2 * lrow);
+                if (r2 == LDC_OK) {
+                    cudaMemset(q, 0, sizeof(float) * ((size_t)B * L.n + 2 * lrow));
+                    *p = q + lrow;
+                }
+                return r2;
+            };
+            A(padded_f(&L.xf));
+            A(padded_f(&L.bf));
+            A(padded_f(&L.rf));
             A(s->dalloc(&L.dpf, (size_t)B * L.N));
         }
     }
@@ -520,6 +541,13 @@ extern "C" int ldc_solver_set_comm(ldc_solver *s, const ldc_comm_ops *ops)
     return LDC_OK;
 }
 
+extern "C" int ldc_solver_set_keep_diverged(ldc_solver *s, int32_t keep)
+{
+    LDC_REQUIRE(s, "ldc_solver_set_keep_diverged: null solver");
+    s->keep_diverged = keep != 0;
+    return LDC_OK;
+}
+
 extern "C" int ldc_solver_num_levels(ldc_solver *s) { return s ? (int)s->levels.size() : 0; }
 
 extern "C" int ldc_solver_counters(ldc_solver *s, int64_t *out3)
@@ -629,6 +657,8 @@ static MgLevel slice_view(const MgLevel &L)
     v.X = L.X + off;
     v.x = L.x ? L.x + off : nullptr;
     v.b = L.b ? L.b + off : nullptr;
+    v.xf = L.xf ? L.xf + off : nullptr;
+    v.bf = L.bf ? L.bf + off : nullptr;
     return v;
 }
 
@@ -663,7 +693,27 @@ template <> struct Lv<float> {
 };
 
 static int level_halo_t(ldc_solver *s, const MgLevel &L, double *v, cudaStream_t st) { return level_halo(s, L, v, st); }
-static int level_halo_t(ldc_solver *, const MgLevel &, float *, cudaStream_t) { return LDC_OK; }  // fp32 cycles are never distributed
+// fp32 level vector of a strip: its rows of 3*nx floats travel as 3*nx/2 doubles (nx is even on
+// every distributed level of a mixed-precision solver, see ldc_solver_create)
+static int level_halo_t(ldc_solver *s, const MgLevel &L, float *v, cudaStream_t st)
+{
+    if (!s->has_comm || s->comm.nranks <= 1 || L.replicated) return LDC_OK;
+    if (s->comm.halo_exchange(s->comm.ctx, reinterpret_cast<double *>(v), 3L * L.nx / 2, L.ny, st) != 0) {
+        set_error("comm halo exchange failed");
+        return LDC_ERR_STATE;
+    }
+    return LDC_OK;
+}
+static int gather_level_t(ldc_solver *s, const MgLevel &L, double *vec, cudaStream_t st) { return gather_level(s, L, vec, st); }
+static int gather_level_t(ldc_solver *s, const MgLevel &L, float *vec, cudaStream_t st)
+{
+    if (!s->has_comm || s->comm.nranks <= 1) return LDC_OK;
+    if (s->comm.allgather(s->comm.ctx, reinterpret_cast<double *>(vec), 3L * L.nx * L.slice_rows / 2, st) != 0) {
+        set_error("comm all-gather failed");
+        return LDC_ERR_STATE;
+    }
+    return LDC_OK;
+}
 
 // y = J_l x or b - J_l x with the true rows of level l; x must be a padded vector (its halo rows
 // are refreshed here for a strip)
@@ -734,7 +784,7 @@ static int remove_mean(ldc_solver *s, const MgLevel &L, T *x, const int32_t *run
     return mg_subtract_mean<T>(L, x, 1, run, s->ks.hcol2, (long)L.nx * L.ny_global, st);
 }
 
-// x must be a padded vector of level l (fp32 cycles: plain vectors, never distributed)
+// x must be a padded vector of level l
 template <typename T>
 static int vcycle(ldc_solver *s, size_t l, const T *b, T *x, const int32_t *run, cudaStream_t st)
 {
@@ -758,12 +808,12 @@ static int vcycle(ldc_solver *s, size_t l, const T *b, T *x, const int32_t *run,
     const MgLevel &C = s->levels[l + 1];
     TRY(level_halo_t(s, L, r, st));   // the last coarse V row of a strip reads the fine row above it
     if (C.replicated && !L.replicated) {
-        // distributed -> replicated (fp64 only): every rank restricts into its rows of the coarse
+        // distributed -> replicated: every rank restricts into its rows of the coarse
         // right-hand side, one all-gather makes it whole, the rest of the cycle runs without
         // communication, and each rank interpolates from its own rows (+ the row below)
         const MgLevel view = slice_view(C);
         TRY(mg_restrict_residual<T>(L, r, view, Lv<T>::b(view), s->batch, run, st));
-        TRY(gather_level(s, C, C.b, st));
+        TRY(gather_level_t(s, C, Lv<T>::b(C), st));
         TRY(vcycle<T>(s, l + 1, Lv<T>::b(C), Lv<T>::x(C), run, st));
         TRY(mg_prolong_add<T>(view, Lv<T>::x(view), L, x, s->batch, run, st));
     } else {
@@ -893,11 +943,18 @@ static int fgmres(ldc_solver *s, const double *rhs, double *y, std::vector<int32
     its.assign(B, 0);
     relres.assign(B, 0.0);
     std::vector<double> cycle_start(B, 1.0);   // relative residual at the start of the restart cycle
-    if (getenv("LDC_DEBUG_KSP")) fprintf(stderr, "[ksp] new solve bnorm=%.3e\n", bnorm[0]);
-    for (int b = 0; b < B; ++b)
-        if (run[b] && !(bnorm[b] > 0.0)) { run[b] = 0; reason[b] = (bnorm[b] == 0.0) ? 3 : -9; }
+    static const bool debug_ksp = getenv("LDC_DEBUG_KSP") != nullptr;   // not on the per-iteration path
+    if (debug_ksp) fprintf(stderr, "[ksp] new solve bnorm=%.3e\n", bnorm[0]);
+    // y = 0 for EVERY requested instance, also those that finish right here with a zero right-hand
+    // side (reason 3): their answer is the zero vector, not whatever the caller's buffer held
     TRY(upload_mask(s, run, s->run_dev, st));
     TRY(vec_zero(y, n, B, s->run_dev, st));
+    {
+        bool dropped = false;
+        for (int b = 0; b < B; ++b)
+            if (run[b] && !(bnorm[b] > 0.0)) { run[b] = 0; reason[b] = (bnorm[b] == 0.0) ? 3 : -9; dropped = true; }
+        if (dropped) TRY(upload_mask(s, run, s->run_dev, st));
+    }
     // r0 = rhs, beta = ||rhs||
     TRY(vec_copy(rhs, s->rres, n, B, s->run_dev, st));
     TRY(norm2_to(s, s->rres, s->ks.nrm2, s->run_dev, st));
@@ -938,7 +995,7 @@ static int fgmres(ldc_solver *s, const double *rhs, double *y, std::vector<int32
                 TRY(upload_mask(s, run, s->run_dev, st));
             }
         }
-        if (getenv("LDC_DEBUG_KSP")) fprintf(stderr, "[ksp] cycle end: its=%d relres=%.3e\n", its[0], relres[0]);
+        if (debug_ksp) fprintf(stderr, "[ksp] cycle end: its=%d relres=%.3e\n", its[0], relres[0]);
         // Stagnation: a full restart cycle that removes less than 10% of the residual will not reach
         // the tolerance within the iteration cap (seen when the Newton iterate has blown up: relres
         // 0.92 -> 0.92 -> 0.92 ...); healthy cycles reduce it by 4x or more.  Failing now instead of
@@ -971,6 +1028,66 @@ static int residual_and_norm(ldc_solver *s, double *norm2_dst, cudaStream_t st)
     TRY(ldc_residual(&s->g, s->X, s->U_old, s->V_old, s->F, norm2_dst, s->res_work,
                      s->opt.residual_variant, st));
     return norm2_dst ? comm_allreduce(s, norm2_dst, s->batch, 0, st) : LDC_OK;
+}
+
+// Building blocks of the (distributed) solve, timed on the solver's own data with CUDA events on
+// the solver's stream: exactly the call sequences the Newton / Krylov loops issue, halo exchanges
+// and all-reduces included.  bench.py uses it for the row-strip table (BASELINE config 5).
+extern "C" int ldc_solver_time_ops(ldc_solver *s, int32_t iters, double *ms_out4, void *stream)
+{
+    LDC_REQUIRE(s && ms_out4 && iters >= 1, "ldc_solver_time_ops: bad argument");
+    LDC_CUDA(cudaEventRecord(s->ev_in, (cudaStream_t)stream));
+    cudaStream_t st = s->stream;
+    LDC_CUDA(cudaStreamWaitEvent(st, s->ev_in, 0));
+    const int B = s->batch;
+    const long n = s->n, vs = (long)B * n;
+    const int nblk = dot_blocks(n);
+    const int kdot = s->m < 15 ? s->m : 15;   // the average Gram-Schmidt width of a GMRES(30) cycle
+    std::vector<int32_t> all(B, 1);
+    TRY(upload_mask(s, all, s->run_dev, st));
+    TRY(build_hierarchy(s, st));              // a valid operator on every level
+    // defined inputs: the basis vectors the timed operations read = the current residual
+    TRY(residual_and_norm(s, s->scal_dev, st));
+    for (int k = 0; k < kdot; ++k) TRY(vec_copy(s->F, s->V + (long)k * vs, n, B, s->run_dev, st));
+    TRY(vec_copy(s->F, s->w, n, B, s->run_dev, st));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    LDC_CUDA(cudaEventCreate(&e0));
+    LDC_CUDA(cudaEventCreate(&e1));
+    int rc = LDC_OK;
+    for (int op = 0; op < 4 && rc == LDC_OK; ++op) {
+        for (int pass = 0; pass < 2 && rc == LDC_OK; ++pass) {   // pass 0 = warm-up
+            const int reps = pass == 0 ? 2 : iters;
+            if (pass == 1) cudaEventRecord(e0, st);
+            for (int i = 0; i < reps && rc == LDC_OK; ++i) {
+                switch (op) {
+                    case 0:   // residual + its norm: halo of X, kernel, all-reduce of sum(F^2)
+                        rc = residual_and_norm(s, s->scal_dev, st);
+                        break;
+                    case 1:   // outer operator: w = J v (halo of v inside)
+                        rc = spmv_outer(s, s->V + (long)(i % 2) * vs, nullptr, s->w, st);
+                        break;
+                    case 2:   // classical Gram-Schmidt projection against kdot basis vectors: fused dots,
+                              // all-reduce of the coefficients, update
+                        rc = vec_multi_dot(s->V, vs, kdot, s->w, n, B, s->run_dev, s->partials, st);
+                        if (rc == LDC_OK) rc = vec_reduce_partials(s->partials, kdot, nblk, B, s->ks.hcol, st);
+                        if (rc == LDC_OK) rc = comm_allreduce(s, s->ks.hcol, (long)B * kdot, 0, st);
+                        break;
+                    default:  // one application of the preconditioner (multigrid cycle)
+                        rc = apply_pc(s, s->V, s->Z, s->run_dev, st);
+                        break;
+                }
+            }
+            if (pass == 1) cudaEventRecord(e1, st);
+        }
+        if (rc == LDC_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = LDC_ERR_CUDA;
+        float ms = 0.f;
+        if (rc == LDC_OK) cudaEventElapsedTime(&ms, e0, e1);
+        ms_out4[op] = (double)ms / iters;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc == LDC_ERR_CUDA) return ldc::cuda_fail(cudaGetLastError(), "ldc_solver_time_ops", __FILE__, __LINE__);
+    return rc;
 }
 
 extern "C" int ldc_solver_linear_solve(ldc_solver *s, const double *rhs_dev, double *y_dev,
@@ -1037,7 +1154,8 @@ extern "C" int ldc_solver_step(ldc_solver *s, const int32_t *active_host, ldc_ne
         if (!run[b]) continue;
         fnorm[b] = sqrt(s->scal_host[b]);
         rep[b].fnorm0 = rep[b].fnorm = fnorm[b];
-        rep[b].function_evaluations = 1;
+        rep[b].function_evaluations = 1;   // residual kernel launches this instance took part in
+        rep[b].jacobian_evaluations = 0;   // FD Jacobian launches (one launch covers all 21 colours)
         ttol[b] = fnorm[b] * o.snes_rtol;
         if (fnorm[b] != fnorm[b]) { rep[b].reason = -4; run[b] = 0; }
         else if (fnorm[b] < o.snes_atol) { rep[b].reason = 2; run[b] = 0; }
@@ -1051,7 +1169,7 @@ extern "C" int ldc_solver_step(ldc_solver *s, const int32_t *active_host, ldc_ne
         TRY(fgmres(s, s->F, s->Y, run, fnorm, kreason, kits, krel, st));
         for (int b = 0; b < B; ++b) {
             if (!run[b]) continue;
-            rep[b].function_evaluations += 21;  // what the coloured FD costs the reference
+            rep[b].jacobian_evaluations += 1;
             rep[b].linear_iterations += kits[b];
             rep[b].ksp_reason = kreason[b];
             s->total_linear_its += kits[b];
@@ -1093,7 +1211,7 @@ extern "C" int ldc_solver_step(ldc_solver *s, const int32_t *active_host, ldc_ne
     // time stepper retries from the old graph, time_stepper.py:23-32)
     std::vector<int32_t> bad(B, 0);
     for (int b = 0; b < B; ++b) bad[b] = (act[b] && rep[b].reason <= 0) ? 1 : 0;
-    if (any(bad)) {
+    if (any(bad) && !s->keep_diverged) {
         TRY(upload_mask(s, bad, s->fin_dev, st));
         TRY(vec_copy(s->X_prev, s->X, n, B, s->fin_dev, st));
     }

@@ -106,6 +106,10 @@ class DeviceBackedGraph(Graph):
         if self._done:
             return
         self._done = True
+        # host arrays are about to be handed out and can be edited in place (``phi[:] = ...``,
+        # ``phi *= 0.5``) without passing through a setter: from here on the device copy cannot be
+        # trusted, so the next solve() uploads the host arrays like it does for a plain Graph
+        self._device_token = None
         from lid_driven_cavity_problem_b200.nonlinear_solver._common import recover_X_device
         U, V, P = [t.cpu().numpy() for t in recover_X_device(self._X_dev, self)]
         Uo, Vo, Po = [t.cpu().numpy() for t in recover_X_device(self._X_old_dev, self)]
@@ -137,6 +141,7 @@ class CudaSolverWrapper(object):
         self.total_linear_iterations = 0
         self.total_newton_iterations = 0
         self.total_function_evaluations = 0
+        self.total_jacobian_evaluations = 0
         if residual_f is not None and getattr(residual_f, '__module__', '').split('.')[-1] != 'cuda_residual_function':
             logger.info("cuda solver: residual_f=%r is ignored, the device residual kernel is used", residual_f)
 
@@ -203,6 +208,11 @@ class CudaSolverWrapper(object):
 
             X_old = torch.empty(3 * nx * ny, dtype=torch.float64, device='cuda')
             _native.check(lib.ldc_solver_get_state(self._handle, _native.ptr(X_old), stream), 'get_state')
+            # options.IGNORE_DIVERGED (read at call time like the reference does): a diverged solve
+            # hands back its last iterate (petsc_solver_wrapper.py:90-103), so the library must not
+            # roll the state back
+            _native.check(lib.ldc_solver_set_keep_diverged(self._handle, 1 if options.IGNORE_DIVERGED else 0),
+                          'ldc_solver_set_keep_diverged')
             report = _native.LdcNewtonReport()
             du = (ctypes.c_double * 1)(0.0)
             _native.check(lib.ldc_solver_step(self._handle, None, ctypes.byref(report), du, stream),
@@ -211,10 +221,12 @@ class CudaSolverWrapper(object):
             self.total_linear_iterations += report.linear_iterations
             self.total_newton_iterations += report.iterations
             self.total_function_evaluations += report.function_evaluations
+            self.total_jacobian_evaluations += report.jacobian_evaluations
 
             if options.SHOW_SOLVER_DETAILS:
-                logger.info("Number of function calls=%s (Newton its=%s, Krylov its=%s)",
-                            report.function_evaluations, report.iterations, report.linear_iterations)
+                logger.info("Number of function calls=%s, FD Jacobian launches=%s (Newton its=%s, Krylov its=%s)",
+                            report.function_evaluations, report.jacobian_evaluations, report.iterations,
+                            report.linear_iterations)
                 text = NONLINEAR_SOLVER_CONVERGENCE_REASONS.get(report.reason, '?')
                 if report.reason > 0:
                     logger.info("Converged with reason: %s", text)

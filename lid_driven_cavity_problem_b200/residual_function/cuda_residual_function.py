@@ -7,7 +7,8 @@ length-3*nx*ny float64 vector.  ``X`` may be
 
 * a numpy array / sequence (what PETSc's callback and scipy's fsolve pass,
   petsc_solver_wrapper.py:42-48, scipy_solver_wrapper.py:35): it is copied to the device
-  through pinned staging buffers, the kernel runs, and a numpy array comes back;
+  by a pipelined library call (pinned staging, H2D, kernel per row block, D2H overlapped:
+  ldc_residual_host, csrc/host_pipeline.cu), and a numpy array comes back;
 * a CUDA ``torch.Tensor`` (float64): the result is a CUDA tensor and nothing crosses PCIe.
 
 Reads exactly what the reference's native residual reads from ``graph``
@@ -116,15 +117,15 @@ def residual_function(X, graph):
     torch = _native.require_cuda()
     if isinstance(X, torch.Tensor):
         return residual_function_device(X, graph)
+    # host arrays in, host array out: ONE library call (ldc_residual_host) that pipelines staging,
+    # H2D, the kernel per row block, D2H and copy-out -- see csrc/host_pipeline.cu
     nx, ny = int(graph.pressure_mesh.nx), int(graph.pressure_mesh.ny)
     n = 3 * nx * ny
-    X_dev = _to_device('X', X, n, torch)
-    U_old_dev = _to_device('U_old', graph.ns_x_mesh.phi_old, (nx - 1) * ny, torch)
-    V_old_dev = _to_device('V_old', graph.ns_y_mesh.phi_old, nx * (ny - 1), torch)
-    F_dev = residual_function_device(X_dev, graph, U_old_dev=U_old_dev, V_old_dev=V_old_dev)
-    out = _pinned('F', n, torch)
-    out.copy_(F_dev, non_blocking=True)
+    Xh = _as_f64('X', X, n)
+    Uh = _as_f64('U_old', graph.ns_x_mesh.phi_old, (nx - 1) * ny)
+    Vh = _as_f64('V_old', graph.ns_y_mesh.phi_old, nx * (ny - 1))
     result = np.empty(n, dtype=np.float64)      # freshly allocated, like the reference backends
-    torch.cuda.current_stream().synchronize()
-    _parallel_copy(result, out.numpy(), torch)  # multi-threaded host copy out of the pinned buffer
+    g = _native.grid_from_graph(graph)
+    rc = _native.lib().ldc_residual_host(g, Xh.ctypes.data, Uh.ctypes.data, Vh.ctypes.data, result.ctypes.data, 0)
+    _native.check(rc, 'ldc_residual_host')
     return result

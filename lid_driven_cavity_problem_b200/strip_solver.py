@@ -22,15 +22,15 @@ logger = logging.getLogger(__name__)
 class CudaStripSolver(object):
     def __init__(self, nx, ny, dt, rho, mi, bc, size_x=1.0, size_y=1.0, comm=None, rank=0, world=1,
                  **solver_options):
-        torch = _native.require_cuda()
-        lib = _native.lib()
-        self.nx, self.ny, self.bc, self.dt = int(nx), int(ny), float(bc), float(dt)
-        self.rank, self.world, self.comm = rank, world, comm
         if ny % world != 0:
             # unequal strips would build different multigrid hierarchies per rank (different
             # sequences of collectives -> a hang); every rank sees the same ny / world, so every
             # rank refuses.  ldc_solver_set_comm checks the same thing collectively.
             raise ValueError("row strips must be equal: ny=%d is not divisible by %d ranks" % (ny, world))
+        torch = _native.require_cuda()
+        lib = _native.lib()
+        self.nx, self.ny, self.bc, self.dt = int(nx), int(ny), float(bc), float(dt)
+        self.rank, self.world, self.comm = rank, world, comm
         self.row_begin, self.row_count = _comm.strip_partition(ny, world, rank, self._align(ny, world))
         g = _native.LdcGrid()
         g.nx, g.ny, g.row_begin, g.row_count, g.batch, g.use_cds = nx, ny, self.row_begin, self.row_count, 1, 0

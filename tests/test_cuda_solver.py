@@ -173,3 +173,120 @@ def test_solver_builder_contract():
         solver_builder.build('nope', None)
     with pytest.raises(TypeError):
         solver_builder.build('cuda', None, no_such_option=1)(make_graph([1.0, 1.0, 8, 8, 1e-2, 1.0, 1.0, 10.0]))
+
+
+def test_converged_state_parity_baseline_grid_256():
+    """north_star tolerance (converged U/V/P to 1e-8 relative) on a BASELINE.json grid: 256x256
+    Re=1000, one pseudo-time step with tight tolerances from a developed state.  A full
+    independent Newton needs ~5 sparse LU factorisations of 196 608 unknowns (~30 s each), so
+    the check is a posteriori: ONE direct Newton correction of the oracle (its FD Jacobian, its
+    residual, sparse LU) at the device solution.  Newton converges quadratically, so that
+    correction is the distance to the oracle's converged state."""
+    from oracle import ldc_oracle as orc
+    from lid_driven_cavity_problem_b200.nonlinear_solver import solver_builder
+    n, bc = 256, 1000.0
+    from lid_driven_cavity_problem_b200.time_stepper import run_simulation
+    # a developed state: two accepted steps of the reference recipe (dt is halved where Newton diverges)
+    g = run_simulation(make_graph([1.0, 1.0, n, n, 1e-2, 1.0, 1.0, bc]), None, solver_builder.build('cuda', None),
+                       max_steps=2)
+    dt = g.dt / 2.0
+    g0 = make_graph([1.0, 1.0, n, n, dt, 1.0, 1.0, bc], None, g.ns_x_mesh.phi, g.ns_y_mesh.phi,
+                    g.pressure_mesh.phi)
+    out = solver_builder.build('cuda', None, **TIGHT)(g0)
+    assert out.newton_report.reason > 0
+    # the oracle's view of that step: phi_old = the entry state, X = the device solution
+    chk = make_graph([1.0, 1.0, n, n, dt, 1.0, 1.0, bc], None, out.ns_x_mesh.phi, out.ns_y_mesh.phi,
+                     out.pressure_mesh.phi)
+    chk.ns_x_mesh.phi_old = np.array(g0.ns_x_mesh.phi)
+    chk.ns_y_mesh.phi_old = np.array(g0.ns_y_mesh.phi)
+    X = orc.create_X(chk.ns_x_mesh.phi, chk.ns_y_mesh.phi, chk.pressure_mesh.phi, chk)
+    F = orc.residual_function(X, chk)
+    mask = orc.jacobian_mask_arrays(n, n, 3)
+    J = orc.fd_jacobian(X, chk, F0=F, mask=mask)
+    delta = orc._direct_solve(mask, J, F)    # X_oracle = X - delta (+ quadratically small terms)
+    U, V, P = out.ns_x_mesh.phi, out.ns_y_mesh.phi, out.pressure_mesh.phi
+    dP = delta[0::3] - delta[0::3].mean()
+    assert np.abs(delta[1::3]).max() < 1e-8 * np.abs(U).max()
+    assert np.abs(delta[2::3]).max() < 1e-8 * np.abs(V).max()
+    assert np.abs(dP).max() < 1e-8 * np.abs(P - P.mean()).max()
+
+
+def test_ignore_diverged_returns_the_diverged_iterate():
+    """options.IGNORE_DIVERGED: the reference hands back whatever SNES ended with
+    (petsc_solver_wrapper.py:90-103).  The returned fields must therefore differ from the entry
+    state -- a rolled-back state would make run_simulation see max|U-U_old| = 0 and report
+    'steady' after a failed step."""
+    from lid_driven_cavity_problem_b200 import options
+    from lid_driven_cavity_problem_b200.nonlinear_solver import solver_builder
+    solve = solver_builder.build('cuda', None)
+    g = make_graph([1.0, 1.0, 64, 64, 1e-2, 1.0, 1.0, 3200.0])
+    options.IGNORE_DIVERGED = True
+    try:
+        res = solve(g)
+    finally:
+        options.IGNORE_DIVERGED = False
+    assert res.newton_report.reason <= 0
+    assert res.steady_state_norm() > 1e-6
+    assert not np.array_equal(res.ns_x_mesh.phi, res.ns_x_mesh.phi_old)
+    assert np.array_equal(res.ns_x_mesh.phi_old, g.ns_x_mesh.phi)
+    # the next ordinary solve on the same wrapper starts from ITS graph, not from the diverged state
+    ok = solve(make_graph([1.0, 1.0, 64, 64, 1e-3, 1.0, 1.0, 3200.0]))
+    assert ok.newton_report.reason > 0
+
+
+def test_in_place_edit_of_a_returned_graph_is_honoured():
+    """A DeviceBackedGraph whose arrays were read can be edited in place (``phi[:] = ...``) without
+    passing through a setter; the next solve must see the edit like it would on a plain Graph."""
+    from lid_driven_cavity_problem_b200.nonlinear_solver import solver_builder
+    solve = solver_builder.build('cuda', None)
+    g1 = solve(make_graph([1.0, 1.0, 32, 32, 1e-2, 1.0, 1.0, 100.0]))
+    a = solve(g1)                                   # resident path, untouched graph
+    g1.ns_x_mesh.phi[:] *= 0.5                      # materialises, then edits in place
+    b = solve(g1)
+    plain = make_graph([1.0, 1.0, 32, 32, 1e-2, 1.0, 1.0, 100.0], None, g1.ns_x_mesh.phi, g1.ns_y_mesh.phi,
+                       g1.pressure_mesh.phi)
+    c = solve(plain)
+    assert not np.allclose(a.ns_x_mesh.phi, b.ns_x_mesh.phi)
+    assert np.array_equal(b.ns_x_mesh.phi, c.ns_x_mesh.phi)
+    assert np.array_equal(b.ns_x_mesh.phi_old, g1.ns_x_mesh.phi)
+
+
+def test_linear_solve_with_zero_rhs_returns_zero():
+    import torch
+    from lid_driven_cavity_problem_b200 import _native
+    lib = _native.lib()
+    g = make_graph([1.0, 1.0, 32, 32, 1e-2, 1.0, 1.0, 100.0])
+    grid = _native.grid_from_graph(g)
+    h = ctypes.c_void_p()
+    _native.check(lib.ldc_solver_create(ctypes.byref(grid), None, ctypes.byref(h)))
+    try:
+        st = _native.current_stream()
+        _native.check(lib.ldc_solver_set_state(h, _native.ptr(torch.ones(3 * 32 * 32, dtype=torch.float64,
+                                                                         device='cuda')), st))
+        rhs = torch.zeros(3 * 32 * 32, dtype=torch.float64, device='cuda')
+        y = torch.full_like(rhs, 7.0)
+        its, reason, rel = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_double()
+        _native.check(lib.ldc_solver_linear_solve(h, _native.ptr(rhs), _native.ptr(y), ctypes.byref(its),
+                                                  ctypes.byref(reason), ctypes.byref(rel), st))
+        assert reason.value == 3 and its.value == 0
+        assert float(y.abs().max()) == 0.0
+    finally:
+        lib.ldc_solver_destroy(h)
+
+
+def test_time_ops_reports_positive_times():
+    from lid_driven_cavity_problem_b200 import _native
+    lib = _native.lib()
+    g = make_graph([1.0, 1.0, 128, 128, 1e-2, 1.0, 1.0, 100.0])
+    grid = _native.grid_from_graph(g)
+    h = ctypes.c_void_p()
+    _native.check(lib.ldc_solver_create(ctypes.byref(grid), None, ctypes.byref(h)))
+    try:
+        import torch
+        _native.check(lib.ldc_solver_set_state(h, _native.ptr(torch.ones(3 * 128 * 128, dtype=torch.float64,
+                                                                         device='cuda')), _native.current_stream()))
+        ms = (ctypes.c_double * 4)()
+        _native.check(lib.ldc_solver_time_ops(h, 5, ms, _native.current_stream()))
+        assert all(0.0 < v < 50.0 for v in ms), list(ms)
+    finally:
+        lib.ldc_solver_destroy(h)

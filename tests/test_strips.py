@@ -25,6 +25,46 @@ def test_strip_partition_covers_the_grid_and_stays_coarsenable():
         assert max(c for _, c in parts) - min(c for _, c in parts) <= (align if ny % (align * world) == 0 else 1)
 
 
+def _plan_levels(nx, ny, row_begin, row_count):
+    import ctypes
+    from lid_driven_cavity_problem_b200 import _native
+    lib = _native.lib()
+    g = _native.LdcGrid()
+    g.nx, g.ny, g.row_begin, g.row_count, g.batch = nx, ny, row_begin, row_count, 1
+    g.dt, g.dx, g.dy, g.rho, g.mi, g.bc = 1e-2, 1.0 / nx, 1.0 / ny, 1.0, 1.0, 1.0
+    opt = _native.LdcSolverOptions()
+    lib.ldc_solver_default_options(ctypes.byref(opt))
+    lev, rep = ctypes.c_int32(), ctypes.c_int32()
+    _native.check(lib.ldc_solver_plan_levels(ctypes.byref(g), ctypes.byref(opt), ctypes.byref(lev),
+                                             ctypes.byref(rep)), 'ldc_solver_plan_levels')
+    return lev.value, rep.value
+
+
+def test_every_rank_of_an_equal_partition_plans_the_same_hierarchy():
+    """The multigrid shape is computed per rank from its own row_begin / row_count
+    (ldc_solver_plan_levels, host arithmetic).  Ranks that disagree would issue different
+    sequences of collectives and hang, so (a) equal strips -- what CudaStripSolver hands out --
+    must agree on every rank, (b) an unequal split is refused on every rank before any device or
+    NCCL work (ValueError here; ldc_solver_set_comm repeats the check collectively)."""
+    from lid_driven_cavity_problem_b200._comm import strip_partition
+    from lid_driven_cavity_problem_b200.strip_solver import CudaStripSolver
+    for nx, ny, world in [(4096, 4096, 8), (4096, 4096, 4), (4096, 4096, 2), (1024, 1024, 8), (1000, 1000, 4),
+                          (1000, 1000, 5), (96, 72, 3), (64, 66, 2), (512, 384, 6), (256, 256, 1)]:
+        assert ny % world == 0
+        align = CudaStripSolver._align(ny, world)
+        plans = {_plan_levels(nx, ny, *strip_partition(ny, world, r, align)) for r in range(world)}
+        assert len(plans) == 1, (nx, ny, world, plans)
+    assert _plan_levels(4096, 4096, 512, 512)[0] >= 6       # a real hierarchy, replicated below some level
+    assert _plan_levels(4096, 4096, 512, 512)[1] > 0
+    # the advisor's example: 1000 rows over 3 ranks = 334/333/333 -> the ranks would disagree ...
+    uneven = {_plan_levels(1000, 1000, *strip_partition(1000, 3, r, 1)) for r in range(3)}
+    assert len(uneven) > 1
+    # ... so the host side refuses it identically on every rank, before touching a device
+    for rank in range(3):
+        with pytest.raises(ValueError, match="equal"):
+            CudaStripSolver(1000, 1000, 1e-2, 1.0, 1.0, 1000.0, rank=rank, world=3)
+
+
 def test_comm_library_exports_every_declared_symbol():
     from lid_driven_cavity_problem_b200 import _comm
     text = open(os.path.join(REPO, 'include', 'ldc_b200_comm.h')).read()
@@ -161,3 +201,76 @@ def test_strip_solver_single_rank_equals_cavity_solver():
     assert np.array_equal(U, ref.ns_x_mesh.phi)
     assert np.array_equal(X[2::3][:n * (n - 1)], ref.ns_y_mesh.phi)
     assert s.krylov_iterations == w.total_linear_iterations
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,fp32", [(2, 0), (2, 1), (4, 1)])
+def test_distributed_strip_solve_equals_single_gpu_solve(world, fp32):
+    """The DISTRIBUTED solver path on one GPU: `world` strips of one 128x128 cavity, one thread per
+    strip, joined by the in-process transport of tests/thread_transport.py (same three calls as the
+    NCCL library).  Exercises the halo rows of fp64 and -- with the mixed-precision cycle -- fp32
+    level vectors, the all-reduced norms / Gram-Schmidt coefficients and the all-gather into the
+    replicated coarse levels.  With tight tolerances every Newton solve converges to ~1e-9, so the
+    distributed and the single-GPU run must land on the same fields (1e-7 relative), whatever the
+    summation order inside the preconditioner."""
+    import torch
+    from thread_transport import run_strips
+    from lid_driven_cavity_problem_b200.strip_solver import CudaStripSolver
+    n, bc, steps = 128, 400.0, 2
+    tight = dict(snes_rtol=1e-13, snes_atol=1e-9, snes_stol=1e-15, ksp_rtol=1e-8, snes_max_it=30, gmres_refine=1,
+                 pc_fp32=fp32)
+    one = CudaStripSolver(n, n, 1e-2, 1.0, 1.0, bc, **tight)
+    one.set_uniform_state()
+    one.run(max_steps=steps)
+    X1 = one.get_state().cpu().numpy()
+    its1 = one.krylov_iterations
+    one.close()
+
+    def strip(rank, comm):
+        s = CudaStripSolver(n, n, 1e-2, 1.0, 1.0, bc, comm=comm, rank=rank, world=world, use_cuda_graphs=0, **tight)
+        try:
+            s.set_uniform_state()
+            s.run(max_steps=steps)
+            torch.cuda.synchronize()
+            return s.row_begin, s.row_count, s.get_state().cpu().numpy(), s.krylov_iterations, s.steps
+        finally:
+            s.close()
+    parts, transport = run_strips(world, strip)
+    assert [p[0] for p in parts] == [r * (n // world) for r in range(world)]
+    X = np.concatenate([p[2] for p in parts])
+    assert all(p[4] == steps for p in parts)
+    assert len({p[3] for p in parts}) == 1                       # every rank took the same decisions
+    assert abs(parts[0][3] - its1) <= max(3, its1 // 10), (parts[0][3], its1)
+    assert transport.calls['halo'] > 0 and transport.calls['allreduce'] > 0 and transport.calls['allgather'] > 0
+    scale = np.abs(X1[1::3]).max()
+    assert np.abs(X[1::3] - X1[1::3]).max() < 1e-7 * scale
+    assert np.abs(X[2::3] - X1[2::3]).max() < 1e-7 * scale
+    P, P1 = X[0::3], X1[0::3]
+    assert np.abs((P - P.mean()) - (P1 - P1.mean())).max() < 1e-7 * np.abs(P1 - P1.mean()).max()
+
+
+@pytest.mark.gpu
+def test_unequal_strip_hierarchies_are_refused_collectively():
+    """ldc_solver_set_comm all-reduces the strip shapes: two strips of 96 and 32 rows of a 128-row
+    cavity plan different hierarchies, and BOTH ranks get an error instead of a hang."""
+    import ctypes
+    from thread_transport import run_strips
+    from lid_driven_cavity_problem_b200 import _native
+    lib = _native.lib()
+    n = 128
+    spans = [(0, 96), (96, 32)]
+
+    def strip(rank, comm):
+        g = _native.LdcGrid()
+        g.nx, g.ny, g.row_begin, g.row_count, g.batch = n, n, spans[rank][0], spans[rank][1], 1
+        g.dt, g.dx, g.dy, g.rho, g.mi, g.bc = 1e-2, 1.0 / n, 1.0 / n, 1.0, 1.0, 100.0
+        h = ctypes.c_void_p()
+        _native.check(lib.ldc_solver_create(ctypes.byref(g), None, ctypes.byref(h)))
+        try:
+            rc = lib.ldc_solver_set_comm(h, comm.ops())
+            return rc, lib.ldc_last_error()
+        finally:
+            lib.ldc_solver_destroy(h)
+    out, _ = run_strips(2, strip)
+    assert all(rc != 0 for rc, _ in out)
+    assert all(b'differ across ranks' in msg for _, msg in out)

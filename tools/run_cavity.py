@@ -59,6 +59,7 @@ def main():
     out = dict(grid='%dx%d' % (nx, ny), Re=args.re, seconds=round(elapsed, 4), steps=len(log),
                newton_its=wrapper.total_newton_iterations, krylov_its=wrapper.total_linear_iterations,
                function_evaluations=wrapper.total_function_evaluations,
+               jacobian_evaluations=wrapper.total_jacobian_evaluations,
                final_dt=log[-1]['dt'] if log else None, final_du=log[-1]['du'] if log else None,
                options=opts)
     if args.ghia:
