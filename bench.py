@@ -8,12 +8,19 @@ time-to-converge of the 1024x1024 Re=1000 steady solve (extra key ``time_to_conv
 One *step* = one residual evaluation F(X) of a 1024x1024 cavity per GPU on the synthetic inputs of
 SURVEY 8(d), inputs resident in HBM, L2-cold by rotating through buffer sets whose total size is
 several times the 126 MB L2.  With N > 1 GPUs the global grid is 1024 x (1024*N), decomposed into
-row strips (one per rank); the one-row halos are read from the neighbour GPUs' peer-mapped memory
-inside the residual kernel (ldc_residual_peer: flag handshake, one launch, no collective; the
-NCCL send/recv + kernel variant is timed next to it under ``halo``).  Weak scaling.
+row strips (one per rank); every strip pushes its boundary rows into the neighbours' ghost rows
+over NVLink with a small side-stream kernel and the residual kernel's edge tiles wait for the
+neighbours' flag words (ldc_residual_peer_step: no collective; the NCCL send/recv + kernel variant
+is timed next to it under ``halo``).  Weak scaling.  The K-step region is measured several times
+and the median region is reported (K x 14 us is too short for a single sample).
 ``e2e`` is the same evaluation through the reference-facing plug-in
-``cuda_residual_function.residual_function(X_numpy, graph)``: host buffers in, host buffer out,
-host<->device copies inside the timed region.
+``cuda_residual_function.residual_function(X_numpy, graph)`` = the C-ABI call ldc_residual_host:
+host buffers in, host buffer out, host<->device copies inside the timed region.
+Extra keys (every rank takes part): ``multi_gpu_parity`` (N > 1: strips vs a single-GPU evaluation,
+distributed solve vs single-GPU solve), ``strips_4096`` (BASELINE config 5: residual / SpMV / dots /
+multigrid cycle of the distributed solver and the whole 4096^2 steady solve, strong scaling),
+``ensemble_512x64`` (config 4).  N = 1 only: ``named_sizes`` (+ CPU baseline per size),
+``other_kernels``, ``time_to_converge`` with the CPU path timed in the same run under a deadline.
 ``--impl reference`` times the reference's own C++-OpenMP residual (oracle/_ref, compiled
 unchanged from c++/residual_function_omp.cpp) on the box's host cores for the same workload.
 """
@@ -518,12 +525,13 @@ def strips_config5(comm, rank, world, peak, n=4096, max_seconds=150.0):
 
 def strip_solve_parity(comm, rank, world, n=256, steps=3):
     """N > 1: the distributed row-strip solve against the single-GPU solve of the same cavity
-    (n x n, Re=1000, `steps` pseudo-time steps, default options), compared on rank 0 after
-    gathering the strips.  The distributed multigrid is algorithmically the single-GPU one, so
-    the two agree to summation-order noise."""
+    (n x n, Re=1000, `steps` pseudo-time steps, tight solver tolerances), compared on rank 0 after
+    gathering the strips: north_star's 1e-8 relative on U, V and P - mean(P)."""
     import torch
     from lid_driven_cavity_problem_b200.strip_solver import CudaStripSolver
-    opts = dict(pc_fp32=0)     # the distributed cycle runs in fp64; compare like with like
+    # tight tolerances: every Newton solve converges to ~1e-9, so the two runs must land on the same
+    # fields whatever the summation order inside the (fp32) preconditioner cycles
+    opts = dict(snes_rtol=1e-13, snes_atol=1e-9, snes_stol=1e-15, ksp_rtol=1e-8, snes_max_it=30, gmres_refine=1)
     dist_solver = CudaStripSolver(n, n, 1e-2, 1.0, 1.0, RE, comm=comm, rank=rank, world=world, **opts)
     dist_solver.set_uniform_state()
     dist_solver.run(max_steps=steps)
@@ -743,16 +751,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_region(step_fn):
+    rendezvous = torch.zeros(1, dtype=torch.float32, device='cuda')
+
+    def timed_region(step_fn, finish=None):
         """EXACTLY `steps` steps between barrier + synchronize on both sides, CUDA events on the
-        launch stream, max over ranks; returns (ms of the region, host enqueue us per step)"""
+        launch stream, max over ranks; returns (ms of the region, host enqueue us per step).
+        `finish` runs after the last step, in front of the end event (the overlapped strip step
+        uses it to make the launch stream wait for its side stream, so that the region covers all
+        the work of its K steps)."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        if world > 1:
+            # the ranks leave the host barrier tens of microseconds apart -- a large share of a
+            # K x 17 us region, spent by the early rank's GPU waiting for the late rank's first
+            # halo.  A tiny in-stream all-reduce in front of the start event lines the GPUs up on
+            # the device timeline (each stream blocks there until every rank's stream arrived).
+            dist.all_reduce(rendezvous)
         e0.record()
         t_host = time.perf_counter()
         for k in range(steps):
             step_fn(k % n_sets)
         enqueue_us = (time.perf_counter() - t_host) / steps * 1e6
+        if finish is not None:
+            finish()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -773,7 +794,8 @@ def main():
     # (each one exactly K steps, bracketed as the contract says) and the MEDIAN region is
     # reported; all of them are listed under `regions_ms_per_step`.
     REGIONS = 7
-    regions = [timed_region(step) for _ in range(REGIONS)]
+    finish = (lambda: peer_strip.join(stream)) if peer_strip is not None else None
+    regions = [timed_region(step, finish) for _ in range(REGIONS)]
     order = sorted(range(REGIONS), key=lambda i: regions[i][0])
     ms_total, host_us = regions[order[REGIONS // 2]]
     # keep the GPU busy long enough for the clock sampler to see it under load
@@ -797,6 +819,7 @@ def main():
         nccl_ms = sorted(timed_region(step_nccl)[0] for _ in range(3))[1] / steps
         # both paths must give the same bits on every rank
         step(0)
+        peer_strip.join(stream)
         F_peer = Fs[0].clone()
         Fs[0].zero_()
         step_nccl(0)
@@ -845,6 +868,8 @@ def main():
         par = {}
         try:
             step(0)
+            if peer_strip is not None:
+                peer_strip.join(stream)
             par["residual_strips_bit_identical_to_single_gpu_evaluation"] = residual_parity_vs_single_gpu(
                 lib, grid, rank, world, Xbuf[0][row:row * (ny_local + 1)], Ud[0], Vd[0], Fs[0], nx, ny_local)
             if not args.no_strips:
@@ -871,42 +896,53 @@ def main():
             dist.destroy_process_group()
         return
 
+    # DRAM bytes of one launch from the committed ncu --set full capture of this kernel (bench.py
+    # cannot run under ncu itself); null when no capture of the current default kernel is on file
+    traffic, traffic_note = None, "no ncu capture on file"
+    try:
+        tr = json.load(open(os.path.join(REPO, 'profiles', 'r2_residual_ring_traffic.json')))
+        traffic = int(tr['dram_bytes_read']) + int(tr['dram_bytes_write'])
+        traffic_note = "%s: read %d B + write %d B in the launch; %s" % (
+            tr['source'], tr['dram_bytes_read'], tr['dram_bytes_write'], tr['note'])
+    except Exception:
+        pass
     line = {
         "metric": "residual_mcells_per_s", "value": value, "unit": "Mcells/s", "n_gpus": world,
         "steps": steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "residual F(X) of a 1024x1024 Re=1000 cavity per GPU (SURVEY 8d synthetic "
-                               "inputs); N>1: row strips of a 1024x(1024*N) grid, the one-row halos read "
-                               "from the neighbour GPUs' memory inside the kernel (flag handshake, "
-                               "no collective)",
+                               "inputs); N>1: row strips of a 1024x(1024*N) grid, every strip pushes its "
+                               "boundary rows into the neighbour GPUs' ghost rows over NVLink (side-stream "
+                               "kernel + flag words), the residual kernel waits on its own flags "
+                               "(no collective)",
                    "grid_per_gpu": [NX, NY], "l2": "L2-cold: rotating %d buffer sets (%.0f MB) > 126 MB L2" % (
                        n_sets, n_sets * res_bytes / 1e6),
-                   "kernel": "residual_march_kernel (flux form, bit-exact arithmetic)"},
+                   "kernel": "residual_ring_kernel (flux form, bit-exact arithmetic; per-warp bulk-copy rings, two cells per lane)",
+                   "timing": "median of %d regions of exactly K steps each (all listed under regions_ms_per_step)" % REGIONS},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full
-                     # (profiles/r1b_residual_march_ncu.csv): reads equal the algorithmic 41.9 MB, the
-                     # 25 MB of F stay in the 126 MB L2 within one launch
-                     "traffic": 43364608 if (NX, NY) == (1024, 1024) else None, "peak_kind": peak_kind,
+                     "traffic": traffic, "traffic_source": traffic_note, "peak_kind": peak_kind,
                      "algorithmic_bytes_per_launch": res_bytes, "kernel_ms": kern_ms},
         "e2e": {"value": NX * NY * world / e2e_s / 1e6, "unit": "Mcells/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_call": e2e_s * 1e3,
                 "api": "cuda_residual_function.residual_function(X_numpy, graph) -> numpy"},
-        "gpu_launches": steps,
+        "gpu_launches": steps if world == 1 or peer_strip is None else 3 * steps,   # N>1: halo push + edge tiles + main kernel
         "clocks": clocks,
+        "regions_ms_per_step": [round(r[0] / steps, 6) for r in regions],
     }
     if world > 1 and peer_strip is None:
         line["halo"] = {"fallback": "NCCL send/recv of the halo rows, then the kernel (CUDA IPC mapping "
                                     "unavailable)", "reason": peer_error}
         line["config"]["workload"] = line["config"]["workload"].replace(
-            "the one-row halos read from the neighbour GPUs' memory inside the kernel (flag handshake, no collective)",
+            "every strip pushes its boundary rows into the neighbour GPUs' ghost rows over NVLink (side-stream "
+            "kernel + flag words), the residual kernel waits on its own flags (no collective)",
             "one-row NCCL halo exchange per evaluation")
     if nccl_ms is not None:
         line["halo"] = {"fused_peer_ms_per_step": ms_step, "nccl_sendrecv_then_kernel_ms_per_step": nccl_ms,
                         "kernel_only_ms": kern_ms, "bit_identical_to_nccl_path": halo_identical,
                         "host_enqueue_us_per_step": round(host_us, 2)}
     line.update(extras)
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:   # the CPU arm belongs to the N = 1 line (torchrun pins workers to one thread)
         v, cores, kind, sample, best = cpu_reference_residual()
         line["cpu_baseline"] = {"value": v, "unit": "Mcells/s", "cores": cores, "kind": kind, "sample": sample,
                                 "best_call_value": best}

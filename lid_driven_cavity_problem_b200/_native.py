@@ -71,6 +71,7 @@ SYMBOLS = {
     'ldc_residual_peer': (ctypes.c_int, [_grid_p, ctypes.POINTER(LdcPeerHalo), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'ldc_peer_ctx_create': (ctypes.c_int, [_i32, ctypes.POINTER(_vp)]),
     'ldc_peer_ctx_destroy': (None, [_vp]),
+    'ldc_peer_ctx_join': (ctypes.c_int, [_vp, _vp]),
     'ldc_residual_peer_step': (ctypes.c_int, [_vp, _grid_p, ctypes.POINTER(LdcPeerHalo), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'ldc_pack_X': (ctypes.c_int, [_grid_p, _vp, _vp, _vp, _vp, _vp]),
     'ldc_unpack_X': (ctypes.c_int, [_grid_p, _vp, _vp, _vp, _vp, _vp]),

@@ -15,6 +15,9 @@
 // so the PCIe link is busy in both directions and the host copies hide behind the DMAs.
 // Staging buffers, device buffers, streams, events and the copy threads are created once per
 // process and reused (grow-only); calls are serialised by a mutex.
+#include <emmintrin.h>
+
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <functional>
@@ -49,7 +52,7 @@ public:
     void copy(void *dst, const void *src, size_t bytes)
     {
         if (bytes < (1u << 20) || n_ == 1) {
-            memcpy(dst, src, bytes);
+            stream_copy(static_cast<char *>(dst), static_cast<const char *>(src), bytes);
             return;
         }
         {
@@ -74,7 +77,30 @@ private:
         const size_t a = per * t;
         if (a >= bytes_) return;
         const size_t len = (a + per <= bytes_) ? per : bytes_ - a;
-        memcpy(dst_ + a, src_ + a, len);
+        stream_copy(dst_ + a, src_ + a, len);
+    }
+    // memcpy with non-temporal stores: the destination is either a pinned staging buffer the DMA
+    // engine reads next or the caller's fresh result array -- neither is read by this core again,
+    // so write-allocating it into the cache only doubles the memory traffic of the copy
+    static void stream_copy(char *dst, const char *src, size_t len)
+    {
+        if (len < (64u << 10) || (reinterpret_cast<uintptr_t>(dst) & 15) != 0) {
+            memcpy(dst, src, len);
+            return;
+        }
+        const size_t body = len & ~size_t(63);
+        for (size_t k = 0; k < body; k += 64) {
+            const __m128i a0 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + k));
+            const __m128i a1 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + k + 16));
+            const __m128i a2 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + k + 32));
+            const __m128i a3 = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + k + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + k), a0);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + k + 16), a1);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + k + 32), a2);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + k + 48), a3);
+        }
+        _mm_sfence();
+        if (body < len) memcpy(dst + body, src + body, len - body);
     }
     void loop(int t)
     {
@@ -126,7 +152,7 @@ struct HostPipeline {
                 if (ranks > 1) nt /= ranks;
             }
             if (const char *e = getenv("LDC_HOST_COPY_THREADS")) nt = atoi(e);
-            if (nt > 8) nt = 8;
+            if (nt > 8) nt = 8;   // measured on the B200 box (16 cores): 4 threads 1.8 ms, 8 threads 1.43 ms, 12-16 no better
             if (nt < 1) nt = 1;
             pool = new CopyPool(nt);
         }
@@ -201,7 +227,16 @@ extern "C" int ldc_residual_host(const ldc_grid *g, const double *X_host, const 
     const size_t n3 = (size_t)3 * nx * ny;
     HostPipeline &p = g_pipe;
     std::lock_guard<std::mutex> guard(p.lock);
+    // LDC_HOST_PROFILE=1: host-clock marks of the pipeline phases on stderr (us since call entry)
+    static const bool profile = getenv("LDC_HOST_PROFILE") != nullptr;
+    const auto t_entry = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what, int b) {
+        if (profile)
+            fprintf(stderr, "[ldc_residual_host] %8.1f us  %s %d\n",
+                    std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_entry).count(), what, b);
+    };
     if (int rc = p.ensure(n3)) return rc;
+    mark("buffers ready", 0);
 
     // row blocks: enough of them to overlap the two DMA directions, each at least ~2 MB of X
     int nb = (int)(n3 * sizeof(double) / (6u << 20));
@@ -247,6 +282,7 @@ extern "C" int ldc_residual_host(const ldc_grid *g, const double *X_host, const 
                                      cudaMemcpyHostToDevice, p.s_in));
         }
         LDC_CUDA(cudaEventRecord(p.ev_in[b], p.s_in));
+        mark("staged + H2D enqueued, block", b);
         // block b-1 has everything now: its own rows (ev_in[b-1], earlier on the same stream) and
         // its upper halo row, the first row of block b
         if (b >= 1)
@@ -258,7 +294,9 @@ extern "C" int ldc_residual_host(const ldc_grid *g, const double *X_host, const 
     for (int b = 0; b < nb; ++b) {
         const long r0 = row_of(b), r1 = row_of(b + 1);
         LDC_CUDA(cudaEventSynchronize(p.ev_out[b]));
+        mark("D2H landed, block", b);
         p.pool->copy(F_host + 3 * nx * r0, p.pin_out + 3 * nx * r0, sizeof(double) * 3 * nx * (r1 - r0));
     }
+    mark("copied out", nb);
     return LDC_OK;
 }

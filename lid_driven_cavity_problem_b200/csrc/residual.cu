@@ -1042,6 +1042,11 @@ static RingArgs plan_ring(const ldc_grid &g, int warps_per_sm)
     RingArgs ra;
     memset(&ra, 0, sizeof(ra));
     ring_strips(g.nx, &ra.n_strips, &ra.cols);
+    if (g.nx <= 64) {   // wall-to-wall strips: see ring_tile
+        ra.n_strips = 1;
+        ra.cols = g.nx;
+        ra.full_row = 1;
+    }
     // Rows per tile: a tile also streams its two halo rows (L2 hits, the neighbour tiles load them
     // too), so tall tiles are cheaper, but the warps should fill the resident slots in whole waves.
     const long slots = (long)warps_per_sm * sm_count();
@@ -1425,11 +1430,20 @@ extern "C" int ldc_residual_peer(const ldc_grid *g, const ldc_peer_halo *peer, c
     return LDC_OK;
 }
 
-// ---- one overlapped evaluation per call: halo push on the context's side stream, kernel on `stream`
+// ---- one overlapped evaluation per call (ldc_residual_peer_step)
+//   side stream (high priority): halo push, then the EDGE tiles of the strip -- the few rows next to
+//                a neighbour, a kernel of ~9 blocks that waits for the neighbours' flag words;
+//   `stream`   : the plain residual kernel (the one ldc_residual runs) over the rows in between,
+//                whose ghost rows are the strip's own edge rows: no waiting, no peer flavour.
+// Two kernels instead of one because the flag wait costs the kernel that contains it its register
+// allocation (168 registers + spills instead of 138-146, every tile flavour ~20 % slower), and
+// because 3 resident blocks of a 168-register kernel leave an SM 1024 free registers -- the push
+// block then has to wait for a residual block to retire, which delays the NEIGHBOUR's edge tiles.
 struct ldc_peer_ctx {
     static constexpr int kEvents = 16;
     cudaStream_t side = nullptr;
-    cudaEvent_t events[kEvents] = {};
+    cudaEvent_t events[kEvents] = {};        // main-stream kernel of evaluation i
+    cudaEvent_t edge_events[kEvents] = {};   // side-stream edge kernel of evaluation i
     long counter = 0;
     int lag = 4;
 };
@@ -1444,8 +1458,10 @@ extern "C" int ldc_peer_ctx_create(int32_t lag, ldc_peer_ctx **out)
     int lo = 0, hi = 0;
     cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically smallest = highest priority
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi);
-    for (int k = 0; k < ldc_peer_ctx::kEvents && e == cudaSuccess; ++k)
+    for (int k = 0; k < ldc_peer_ctx::kEvents && e == cudaSuccess; ++k) {
         e = cudaEventCreateWithFlags(&c->events[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->edge_events[k], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
         ldc_peer_ctx_destroy(c);
         return ldc::cuda_fail(e, "ldc_peer_ctx_create", __FILE__, __LINE__);
@@ -1457,10 +1473,20 @@ extern "C" int ldc_peer_ctx_create(int32_t lag, ldc_peer_ctx **out)
 extern "C" void ldc_peer_ctx_destroy(ldc_peer_ctx *c)
 {
     if (!c) return;
-    for (int k = 0; k < ldc_peer_ctx::kEvents; ++k)
+    for (int k = 0; k < ldc_peer_ctx::kEvents; ++k) {
         if (c->events[k]) cudaEventDestroy(c->events[k]);
+        if (c->edge_events[k]) cudaEventDestroy(c->edge_events[k]);
+    }
     if (c->side) cudaStreamDestroy(c->side);
     delete c;
+}
+
+extern "C" int ldc_peer_ctx_join(ldc_peer_ctx *c, void *stream)
+{
+    LDC_REQUIRE(c, "ldc_peer_ctx_join: null context");
+    if (c->counter > 0)
+        LDC_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, c->edge_events[(c->counter - 1) % ldc_peer_ctx::kEvents], 0));
+    return LDC_OK;
 }
 
 extern "C" int ldc_residual_peer_step(ldc_peer_ctx *c, const ldc_grid *g, const ldc_peer_halo *peer,
@@ -1468,22 +1494,63 @@ extern "C" int ldc_residual_peer_step(ldc_peer_ctx *c, const ldc_grid *g, const 
                                       double *F_dev, double *norm2_dev, double *work_dev, void *stream)
 {
     LDC_REQUIRE(c, "ldc_residual_peer_step: null context");
+    if (int rc = validate_grid(g, false)) return rc;
+    if (int rc = validate_peer(g, peer, "ldc_residual_peer_step")) return rc;
+    LDC_REQUIRE(X_dev && U_old_dev && V_old_dev && F_dev, "ldc_residual_peer_step: null device pointer");
     const long i = c->counter++;
+    const int slot = (int)(i % ldc_peer_ctx::kEvents);
     static const int dbg = ring_env_int("LDC_PEER_DEBUG", 0);
-    // Flow control: push(i) waits for the residual kernel of evaluation i-lag of THIS strip.  That
-    // kernel needed the neighbours' push(i-lag), which in turn waited for their kernels of
-    // evaluation i-2*lag: when push(i) overwrites a ghost row, the neighbour has finished every
-    // evaluation up to i-2*lag, so rotating more than 2*lag X buffers is safe -- and the event
-    // waited for is `lag` evaluations old, so the pushes are never held up in steady state.
+    cudaStream_t s = (cudaStream_t)stream;
+    // Flow control.  (a) The side stream is in order: push(i) follows this strip's edge kernel of
+    // evaluation i-1, which needed the neighbours' push(i-1), which followed THEIR edge kernel of
+    // evaluation i-2 -- so when push(i) overwrites a ghost row, the neighbour has finished reading
+    // every ghost row up to evaluation i-2 (two rotating X buffers suffice).  (b) push(i) also waits
+    // for this strip's main kernel of evaluation i-lag, which bounds how far the side stream runs
+    // ahead of `stream`; that event is `lag` evaluations old, so it never holds a push up.
     if (i >= c->lag && !(dbg & 64))
         LDC_CUDA(cudaStreamWaitEvent(c->side, c->events[(i - c->lag) % ldc_peer_ctx::kEvents], 0));
+    const bool has_prev = peer->prev_ghost != nullptr, has_next = peer->next_ghost != nullptr;
+    const int n_edges = (has_prev ? 1 : 0) + (has_next ? 1 : 0);
+    const int edge = ring_eligible(*g, X_dev, U_old_dev, V_old_dev, F_dev) ? ring_edge_rows(*g, n_edges) : 0;
+    if (edge == 0 || norm2_dev || (dbg & 32)) {
+        // thin strips, odd nx, a fused norm: push + ONE kernel that contains the waits
+        if (!(dbg & 16))
+            if (int rc = ldc_residual_peer_push(g, peer, X_dev, c->side)) return rc;
+        if (int rc = ldc_residual_peer(g, peer, X_dev, U_old_dev, V_old_dev, F_dev, norm2_dev, work_dev, s)) return rc;
+        LDC_CUDA(cudaEventRecord(c->events[slot], s));
+        LDC_CUDA(cudaEventRecord(c->edge_events[slot], s));
+        return LDC_OK;
+    }
+    // side stream: push, then the edge tiles
     if (!(dbg & 16))
         if (int rc = ldc_residual_peer_push(g, peer, X_dev, c->side)) return rc;
-    if (dbg & 128) {   // experiment: the plain kernel on the local ghost rows instead of the peer kernel
-        if (int rc = ldc_residual(g, X_dev, U_old_dev, V_old_dev, F_dev, norm2_dev, work_dev, 0, stream)) return rc;
-    } else if (int rc = ldc_residual_peer(g, peer, X_dev, U_old_dev, V_old_dev, F_dev, norm2_dev, work_dev, stream)) {
-        return rc;
+    {
+        int wps = 0;
+        if (int rc = ring_warps_per_sm(*g, false, true, &wps)) return rc;
+        RingArgs ra = plan_ring_peer(*g, has_prev, has_next, wps);
+        ra.n_row_tiles = n_edges;            // only the short tiles next to the neighbours (they come first)
+        ra.per_instance = (long)ra.n_strips * n_edges;
+        ra.total = ra.per_instance;
+        RingGhost gh;
+        memset(&gh, 0, sizeof(gh));
+        gh.prev_word = has_prev ? peer->my_flags + 0 : nullptr;
+        gh.next_word = has_next ? peer->my_flags + 1 : nullptr;
+        gh.epoch = peer->epoch;
+        gh.status = peer->status_dev;
+        if (int rc = ring_launch(*g, ra, gh, true, X_dev, U_old_dev, V_old_dev, F_dev, nullptr, c->side)) return rc;
+        LDC_CUDA(cudaEventRecord(c->edge_events[slot], c->side));
     }
-    if (!(dbg & 64)) LDC_CUDA(cudaEventRecord(c->events[i % ldc_peer_ctx::kEvents], (cudaStream_t)stream));
+    // `stream`: the rows in between with the plain kernel
+    {
+        const int e_lo = has_prev ? edge : 0, e_hi = has_next ? edge : 0;
+        ldc_grid sub = *g;
+        sub.row_begin = g->row_begin + e_lo;
+        sub.row_count = g->row_count - e_lo - e_hi;
+        const long nx = g->nx;
+        if (int rc = ldc_residual(&sub, X_dev + 3 * nx * e_lo, U_old_dev + (nx - 1) * e_lo, V_old_dev + nx * e_lo,
+                                  F_dev + 3 * nx * e_lo, nullptr, nullptr, 0, s))
+            return rc;
+        if (!(dbg & 64)) LDC_CUDA(cudaEventRecord(c->events[slot], s));
+    }
     return LDC_OK;
 }

@@ -44,6 +44,7 @@ struct RingArgs {
     long u_off;                  // U_old index of the call's first row relative to the (16-byte aligned) U_old base
     long partial_off;            // first slot of this launch in the sum(F^2) partials
     int debug;                   // peer kernel experiments: 1 = no flag waits
+    int full_row;                // nx <= 64: ONE strip from wall to wall, all 32 lanes own two cells (no halo lane)
 };
 
 // Per-cavity constants, evaluated on the host with the IEEE operations the device helpers use
@@ -177,8 +178,13 @@ __device__ __forceinline__ double ring_tile(const ldc_grid &g, const RingPhys &r
     uint64_t *bars = reinterpret_cast<uint64_t *>(fbuf + (BULK_STORE ? ring::kFBufs * ring::kFSlab : 0));
 
     // ---- geometry of this warp's strip
-    const int ia = c0 - 2 + 2 * lane;                 // first cell of the lane; second ia+1, east ia+2
-    const bool writer = lane >= 1 && 2 * lane <= cw;  // lanes 1..cw/2 own the strip's columns
+    // Narrow grids (nx <= 64, e.g. the 64x64 cavities of a Reynolds ensemble): one strip from wall to
+    // wall, lane L owns cells 2L, 2L+1 and lane 0 evaluates the west-wall face itself instead of
+    // being the halo lane -- a 64-column row is one warp instead of two half-empty ones.
+    const bool full = !INTERIOR && ra.full_row != 0;
+    const int lo = full ? 2 * lane : 2 * lane - 2;    // lane's first column relative to c0
+    const int ia = c0 + lo;                           // first cell of the lane; second ia+1, east ia+2
+    const bool writer = full ? (lo < cw) : (lane >= 1 && 2 * lane <= cw);   // lanes that own columns of the strip
     const bool ab_in = INTERIOR || (ia >= 0 && ia < nx);           // nx even: both cells or none
     const bool e_in = INTERIOR || (ia + 2 < nx);
     const bool b_ucol = INTERIOR || (ia + 1 >= 0 && ia + 1 < nx - 1);   // cell b's U slot is a real U
@@ -320,17 +326,17 @@ __device__ __forceinline__ double ring_tile(const ldc_grid &g, const RingPhys &r
         if (writer) {
             const bool staged = ((u_rd + ucnt + 1) & ~1L) <= ra.u_total;
             if (staged) {
-                const double *uq = stg + ring::kXSlab + (2 * lane - 2) + (int)(u_rd & 1);
+                const double *uq = stg + ring::kXSlab + lo + (int)(u_rd & 1);
                 Uold_a = uq[0];
                 if (b_ucol) Uold_b = uq[1];
             } else {
-                const double *uq = U_base + u_rd + (2 * lane - 2);
+                const double *uq = U_base + u_rd + lo;
                 Uold_a = __ldg(uq);
                 if (b_ucol) Uold_b = __ldg(uq + 1);
             }
             if (INTERIOR || jg < ny - 1) {
                 const double2 vv =
-                    *reinterpret_cast<const double2 *>(stg + ring::kXSlab + ring::kUSlab + (2 * lane - 2));
+                    *reinterpret_cast<const double2 *>(stg + ring::kXSlab + ring::kUSlab + lo);
                 Vold_a = vv.x;
                 Vold_b = vv.y;
             }
@@ -367,11 +373,20 @@ __device__ __forceinline__ double ring_tile(const ldc_grid &g, const RingPhys &r
         const double CUe_b = dmul(C.bU, rp.dy);
 
         // ---- west face of a = east face of the previous lane's b
-        const double AUw_a = shfl_up1(AUe_b);
-        const double DUw_a = shfl_up1(DUe_b);
-        const double AVw_a = shfl_up1(AVe_b);
-        const double DVw_a = shfl_up1(DVe_b);
-        const double CUw_a = shfl_up1(CUe_b);
+        double AUw_a = shfl_up1(AUe_b);
+        double DUw_a = shfl_up1(DUe_b);
+        double AVw_a = shfl_up1(AVe_b);
+        double DVw_a = shfl_up1(DVe_b);
+        double CUw_a = shfl_up1(CUe_b);
+        if (full && lane == 0) {
+            // the west-wall face of cell 0: what a halo lane holding two zero (outside) cells west
+            // of it computes as ITS east face of b -- same expressions, same bits
+            AUw_a = fx.adv_x(C.aU, 0.0, C.aU, 0.0);
+            DUw_a = fx.dif_x(C.aU, 0.0);
+            AVw_a = fx.adv_x(0.0, 0.0, C.aV, 0.0);
+            DVw_a = fx.dif_x(C.aV, 0.0);
+            CUw_a = dmul(0.0, rp.dy);
+        }
 
         if (writer) {
             const bool v_row = INTERIOR || jg < ny - 1;
@@ -413,7 +428,7 @@ __device__ __forceinline__ double ring_tile(const ldc_grid &g, const RingPhys &r
                 b2 = rawV_b;
             }
             if (BULK_STORE) {
-                double *fq = fbuf + fslot * ring::kFSlab + 6 * (lane - 1);
+                double *fq = fbuf + fslot * ring::kFSlab + 3 * lo;
                 *reinterpret_cast<double2 *>(fq) = make_double2(a0, a1);
                 *reinterpret_cast<double2 *>(fq + 2) = make_double2(a2, b0);
                 *reinterpret_cast<double2 *>(fq + 4) = make_double2(b1, b2);
