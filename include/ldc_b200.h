@@ -121,21 +121,22 @@ LDC_API int ldc_residual_peer_push(const ldc_grid *g, const ldc_peer_halo *peer,
 LDC_API int ldc_residual_peer(const ldc_grid *g, const ldc_peer_halo *peer, const double *X_dev,
                       const double *U_old_dev, const double *V_old_dev, double *F_dev,
                       double *norm2_dev, double *work_dev, void *stream);
-/* One evaluation in one call, overlapped on two streams.  The context owns a high-priority side
- * stream that carries the push and then a SMALL kernel over the strip's edge tiles (the few rows
- * next to a neighbour strip; it contains the flag waits); `stream` carries the plain kernel of
- * ldc_residual over the rows in between, whose ghost rows are the strip's own edge rows.  (One
+/* One evaluation in one call, overlapped on three streams.  The context owns two high-priority
+ * streams: one carries the push, the other a SMALL kernel over the strip's edge tiles (the few
+ * rows next to a neighbour strip; it contains the flag waits); `stream` carries the plain kernel
+ * of ldc_residual over the rows in between, whose ghost rows are the strip's own edge rows.  (One
  * kernel containing the waits is ~20 % slower on every tile, and its register footprint keeps
  * the push block from becoming resident next to it; thin strips, odd nx or a fused norm fall
- * back to push + ldc_residual_peer.)  F is complete when BOTH streams have finished the
- * evaluation: call ldc_peer_ctx_join(ctx, stream) before consuming F on `stream` (bench.py does
- * so once, in front of the event that ends a timed region).  Meant for loops over rotating X
- * buffers whose contents are final before the loop starts: the side stream is not ordered after
- * work queued on `stream`, except that push(i) waits for this strip's main kernel of evaluation
- * i-lag (bounded run-ahead).  Ghost rows are protected by the order of the side streams: push(i)
- * follows this strip's edge kernel i-1, which needed the neighbours' push(i-1), which followed
- * their edge kernel i-2 -- at least two rotating X buffers.  A caller whose X is produced on
- * `stream` between evaluations uses ldc_residual_peer_push / ldc_residual_peer with its own event. */
+ * back to push + ldc_residual_peer.)  F is complete when `stream` AND the edge stream have
+ * finished the evaluation: call ldc_peer_ctx_join(ctx, stream) before consuming F on `stream`
+ * (bench.py does so once, in front of the event that ends a timed region).  Meant for loops over
+ * rotating X buffers whose contents are final before the loop starts: the context's streams are
+ * not ordered after work queued on `stream`, except that push(i) waits for this strip's main and
+ * edge kernels of evaluation i-lag.  That edge kernel needed the neighbours' push(i-lag), which
+ * waited for their edge kernels of evaluation i-2*lag, so a ghost row is never overwritten while
+ * a neighbour still reads it as long as more than 2*lag X buffers rotate.  A caller whose X is
+ * produced on `stream` between evaluations uses ldc_residual_peer_push / ldc_residual_peer with
+ * its own event. */
 typedef struct ldc_peer_ctx ldc_peer_ctx;
 LDC_API int ldc_peer_ctx_create(int32_t lag, ldc_peer_ctx **out);
 LDC_API void ldc_peer_ctx_destroy(ldc_peer_ctx *ctx);

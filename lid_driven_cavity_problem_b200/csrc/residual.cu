@@ -1030,14 +1030,16 @@ static void ring_strips(int nx, int *n_strips, int *cols)
 }
 
 // uniform row tiles over the rows of `g` (ldc_residual, and the rows between the edge tiles of a strip)
-static RingArgs plan_ring(const ldc_grid &g, int warps_per_sm)
+// `reserved`: warp slots of the device that concurrent work occupies (the edge-tile kernel of
+// ldc_residual_peer_step): the tiles are sized to fill the REST in whole waves
+static RingArgs plan_ring(const ldc_grid &g, int warps_per_sm, int reserved = 0)
 {
     // the plan only depends on the grid shape: keep the last one
-    struct Key { int nx, rows, batch, wps; };
-    static thread_local Key last_key{0, 0, 0, 0};
+    struct Key { int nx, rows, batch, wps, reserved; };
+    static thread_local Key last_key{0, 0, 0, 0, 0};
     static thread_local RingArgs last;
     if (last_key.nx == g.nx && last_key.rows == g.row_count && last_key.batch == g.batch &&
-        last_key.wps == warps_per_sm)
+        last_key.wps == warps_per_sm && last_key.reserved == reserved)
         return last;
     RingArgs ra;
     memset(&ra, 0, sizeof(ra));
@@ -1049,7 +1051,8 @@ static RingArgs plan_ring(const ldc_grid &g, int warps_per_sm)
     }
     // Rows per tile: a tile also streams its two halo rows (L2 hits, the neighbour tiles load them
     // too), so tall tiles are cheaper, but the warps should fill the resident slots in whole waves.
-    const long slots = (long)warps_per_sm * sm_count();
+    long slots = (long)warps_per_sm * sm_count() - reserved;
+    if (slots < warps_per_sm) slots = warps_per_sm;
     int best_rows = g.row_count < 4 ? g.row_count : 4;
     if (ring_tuning().rows > 0) {
         best_rows = ring_tuning().rows < g.row_count ? ring_tuning().rows : g.row_count;
@@ -1071,7 +1074,7 @@ static RingArgs plan_ring(const ldc_grid &g, int warps_per_sm)
     if (getenv("LDC_RING_VERBOSE"))
         fprintf(stderr, "[ldc] ring plan %dx%d x%d: %d strips of %d columns, %d row tiles of %d rows, %ld warps on %ld slots\n",
                 g.nx, g.row_count, g.batch, ra.n_strips, ra.cols, ra.n_row_tiles, ra.rows, ra.total, slots);
-    last_key = Key{g.nx, g.row_count, g.batch, warps_per_sm};
+    last_key = Key{g.nx, g.row_count, g.batch, warps_per_sm, reserved};
     last = ra;
     return ra;
 }
@@ -1138,7 +1141,8 @@ static RingArgs plan_ring_peer(const ldc_grid &g, bool has_prev, bool has_next, 
 
 // one launch of the ring kernel
 static int ring_launch(const ldc_grid &g, const RingArgs &ra, const RingGhost &gh, bool peer, const double *X,
-                       const double *U_base, const double *V_old, double *F, double *partials, cudaStream_t s)
+                       const double *U_base, const double *V_old, double *F, double *partials, cudaStream_t s,
+                       bool allow_pdl = true)
 {
     const bool pow2 = is_pow2_double(g.dx) && is_pow2_double(g.dy);
     const bool fast = pow2 && g.rho == 1.0 && g.mi == 1.0;
@@ -1157,7 +1161,9 @@ static int ring_launch(const ldc_grid &g, const RingArgs &ra, const RingGhost &g
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = ring_tuning().pdl ? 1 : 0;
+    // kernels that contain flag waits are never pre-launched: resident early, they would spin for
+    // words that cannot have arrived yet on SM slots the running kernel needs
+    cfg.numAttrs = (ring_tuning().pdl && allow_pdl && !peer) ? 1 : 0;
     LDC_CUDA(cudaLaunchKernelEx(&cfg, rl->fn, g, rp, ra, gh, X, U_base, V_old, F, partials));
     return LDC_OK;
 }
@@ -1431,8 +1437,12 @@ extern "C" int ldc_residual_peer(const ldc_grid *g, const ldc_peer_halo *peer, c
 }
 
 // ---- one overlapped evaluation per call (ldc_residual_peer_step)
-//   side stream (high priority): halo push, then the EDGE tiles of the strip -- the few rows next to
-//                a neighbour, a kernel of ~9 blocks that waits for the neighbours' flag words;
+//   push stream (high priority): the halo push;
+//   edge stream (high priority): the EDGE tiles of the strip -- the few rows next to a neighbour, a
+//                kernel of ~9 blocks that waits for the neighbours' flag words.  Its own stream:
+//                queued behind the push (launch + NVLink round trip + system-scope flush, ~8 us)
+//                the pair would take longer per evaluation than the 14 us main kernel (measured:
+//                20 us per step with push and edge tiles on one stream);
 //   `stream`   : the plain residual kernel (the one ldc_residual runs) over the rows in between,
 //                whose ghost rows are the strip's own edge rows: no waiting, no peer flavour.
 // Two kernels instead of one because the flag wait costs the kernel that contains it its register
@@ -1441,7 +1451,7 @@ extern "C" int ldc_residual_peer(const ldc_grid *g, const ldc_peer_halo *peer, c
 // block then has to wait for a residual block to retire, which delays the NEIGHBOUR's edge tiles.
 struct ldc_peer_ctx {
     static constexpr int kEvents = 16;
-    cudaStream_t side = nullptr;
+    cudaStream_t side = nullptr, edge = nullptr;   // push stream, edge-tile stream
     cudaEvent_t events[kEvents] = {};        // main-stream kernel of evaluation i
     cudaEvent_t edge_events[kEvents] = {};   // side-stream edge kernel of evaluation i
     long counter = 0;
@@ -1458,6 +1468,7 @@ extern "C" int ldc_peer_ctx_create(int32_t lag, ldc_peer_ctx **out)
     int lo = 0, hi = 0;
     cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);   // hi = numerically smallest = highest priority
     if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->edge, cudaStreamNonBlocking, hi);
     for (int k = 0; k < ldc_peer_ctx::kEvents && e == cudaSuccess; ++k) {
         e = cudaEventCreateWithFlags(&c->events[k], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->edge_events[k], cudaEventDisableTiming);
@@ -1478,6 +1489,7 @@ extern "C" void ldc_peer_ctx_destroy(ldc_peer_ctx *c)
         if (c->edge_events[k]) cudaEventDestroy(c->edge_events[k]);
     }
     if (c->side) cudaStreamDestroy(c->side);
+    if (c->edge) cudaStreamDestroy(c->edge);
     delete c;
 }
 
@@ -1501,18 +1513,20 @@ extern "C" int ldc_residual_peer_step(ldc_peer_ctx *c, const ldc_grid *g, const 
     const int slot = (int)(i % ldc_peer_ctx::kEvents);
     static const int dbg = ring_env_int("LDC_PEER_DEBUG", 0);
     cudaStream_t s = (cudaStream_t)stream;
-    // Flow control.  (a) The side stream is in order: push(i) follows this strip's edge kernel of
-    // evaluation i-1, which needed the neighbours' push(i-1), which followed THEIR edge kernel of
-    // evaluation i-2 -- so when push(i) overwrites a ghost row, the neighbour has finished reading
-    // every ghost row up to evaluation i-2 (two rotating X buffers suffice).  (b) push(i) also waits
-    // for this strip's main kernel of evaluation i-lag, which bounds how far the side stream runs
-    // ahead of `stream`; that event is `lag` evaluations old, so it never holds a push up.
-    if (i >= c->lag && !(dbg & 64))
+    // Flow control: push(i) waits for this strip's main kernel AND edge kernel of evaluation
+    // i-lag.  That edge kernel needed the neighbours' push(i-lag), which waited for THEIR edge
+    // kernels of evaluation i-2*lag: when push(i) overwrites a ghost row, the neighbour has
+    // finished reading every ghost row up to evaluation i-2*lag, so rotating more than 2*lag X
+    // buffers is safe.  Both events are `lag` evaluations old and never hold a push up in steady
+    // state; they also bound how far the push stream runs ahead of the other two.
+    if (i >= c->lag && !(dbg & 64)) {
         LDC_CUDA(cudaStreamWaitEvent(c->side, c->events[(i - c->lag) % ldc_peer_ctx::kEvents], 0));
+        LDC_CUDA(cudaStreamWaitEvent(c->side, c->edge_events[(i - c->lag) % ldc_peer_ctx::kEvents], 0));
+    }
     const bool has_prev = peer->prev_ghost != nullptr, has_next = peer->next_ghost != nullptr;
     const int n_edges = (has_prev ? 1 : 0) + (has_next ? 1 : 0);
     const int edge = ring_eligible(*g, X_dev, U_old_dev, V_old_dev, F_dev) ? ring_edge_rows(*g, n_edges) : 0;
-    if (edge == 0 || norm2_dev || (dbg & 32)) {
+    if (edge == 0 || norm2_dev || (dbg & 256)) {
         // thin strips, odd nx, a fused norm: push + ONE kernel that contains the waits
         if (!(dbg & 16))
             if (int rc = ldc_residual_peer_push(g, peer, X_dev, c->side)) return rc;
@@ -1521,34 +1535,44 @@ extern "C" int ldc_residual_peer_step(ldc_peer_ctx *c, const ldc_grid *g, const 
         LDC_CUDA(cudaEventRecord(c->edge_events[slot], s));
         return LDC_OK;
     }
-    // side stream: push, then the edge tiles
+    // push stream: the halo push; edge stream: the edge tiles
     if (!(dbg & 16))
         if (int rc = ldc_residual_peer_push(g, peer, X_dev, c->side)) return rc;
+    int wps_edge = 0;
+    if (int rc = ring_warps_per_sm(*g, false, true, &wps_edge)) return rc;
+    RingArgs ea = plan_ring_peer(*g, has_prev, has_next, wps_edge);
+    ea.n_row_tiles = n_edges;            // only the short tiles next to the neighbours (they come first)
+    ea.per_instance = (long)ea.n_strips * n_edges;
+    ea.total = ea.per_instance;
     {
-        int wps = 0;
-        if (int rc = ring_warps_per_sm(*g, false, true, &wps)) return rc;
-        RingArgs ra = plan_ring_peer(*g, has_prev, has_next, wps);
-        ra.n_row_tiles = n_edges;            // only the short tiles next to the neighbours (they come first)
-        ra.per_instance = (long)ra.n_strips * n_edges;
-        ra.total = ra.per_instance;
         RingGhost gh;
         memset(&gh, 0, sizeof(gh));
         gh.prev_word = has_prev ? peer->my_flags + 0 : nullptr;
         gh.next_word = has_next ? peer->my_flags + 1 : nullptr;
         gh.epoch = peer->epoch;
         gh.status = peer->status_dev;
-        if (int rc = ring_launch(*g, ra, gh, true, X_dev, U_old_dev, V_old_dev, F_dev, nullptr, c->side)) return rc;
-        LDC_CUDA(cudaEventRecord(c->edge_events[slot], c->side));
+        // NO programmatic dependent launch for the edge kernels: with it the edge kernel of the next
+        // evaluation becomes resident early and spins for flag words that cannot have arrived yet,
+        // on SM slots the main kernel needs (measured, 2 GPUs: 18.5 us per step with, 14.8 without)
+        if (int rc = ring_launch(*g, ea, gh, true, X_dev, U_old_dev, V_old_dev, F_dev, nullptr, c->edge, false))
+            return rc;
+        LDC_CUDA(cudaEventRecord(c->edge_events[slot], c->edge));
     }
-    // `stream`: the rows in between with the plain kernel
+    // `stream`: the rows in between with the plain kernel, its tiles sized for the warp slots the
+    // edge blocks leave free
     {
         const int e_lo = has_prev ? edge : 0, e_hi = has_next ? edge : 0;
         ldc_grid sub = *g;
         sub.row_begin = g->row_begin + e_lo;
         sub.row_count = g->row_count - e_lo - e_hi;
         const long nx = g->nx;
-        if (int rc = ldc_residual(&sub, X_dev + 3 * nx * e_lo, U_old_dev + (nx - 1) * e_lo, V_old_dev + nx * e_lo,
-                                  F_dev + 3 * nx * e_lo, nullptr, nullptr, 0, s))
+        int wps = 0;
+        if (int rc = ring_warps_per_sm(sub, false, false, &wps)) return rc;
+        const RingArgs ra = plan_ring(sub, wps, (int)(((ea.total + 3) / 4) * 4));
+        RingGhost no_ghost;
+        memset(&no_ghost, 0, sizeof(no_ghost));
+        if (int rc = ring_launch(sub, ra, no_ghost, false, X_dev + 3 * nx * e_lo, U_old_dev + (nx - 1) * e_lo,
+                                 V_old_dev + nx * e_lo, F_dev + 3 * nx * e_lo, nullptr, s))
             return rc;
         if (!(dbg & 64)) LDC_CUDA(cudaEventRecord(c->events[slot], s));
     }

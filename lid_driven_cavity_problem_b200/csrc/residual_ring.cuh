@@ -135,23 +135,26 @@ struct RingGhost {
     int32_t *status;
 };
 
-__device__ __forceinline__ unsigned long long ld_flag_acquire(const unsigned long long *p)
+__device__ __forceinline__ unsigned long long ld_flag_relaxed(const unsigned long long *p)
 {
     unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// bounded wait (a few seconds): a lost neighbour must not hang the device.  On success the ghost
-// row is ordered before the bulk copy that follows (acquire, then generic -> async proxy fence).
+// bounded wait (a few seconds): a lost neighbour must not hang the device.  The word is polled
+// with relaxed loads and ONE system-scope acquire fence follows the successful poll (pairs with the
+// release store of halo_push_kernel); then the ghost row is ordered before the bulk copy that
+// follows (generic -> async proxy fence).  Measured: neither fence costs anything per step.
 __device__ __forceinline__ void wait_ghost(const unsigned long long *word, unsigned long long epoch,
                                            int32_t *status)
 {
     for (long it = 0; it < (1L << 24); ++it) {
-        if (ld_flag_acquire(word) >= epoch) {
+        if (ld_flag_relaxed(word) >= epoch) {
+            asm volatile("fence.acquire.sys;" ::: "memory");
             asm volatile("fence.proxy.async.global;" ::: "memory");
             return;
         }
-        __nanosleep(it < 64 ? 20 : 250);
+        __nanosleep(it < 16 ? 100 : 400);
     }
     if (status) atomicExch(status, 1);
 }
