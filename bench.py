@@ -723,7 +723,7 @@ def main():
 
     if region is not None:
         peer_strip = peer_halo.PeerStripResidual(grid, region[0], region[1], region[2], ny_local, ny_local, n_sets)
-        peer_launch = [peer_strip.bind_overlapped(k, Ud[k], Vd[k], Fs[k], lag=4) for k in range(n_sets)]
+        peer_launch = [peer_strip.bind_overlapped(k, Ud[k], Vd[k], Fs[k], lag=3) for k in range(n_sets)]
 
     def step_nccl(k):
         # baseline: one NCCL group (both neighbours) issued from C on the launch stream, then the
@@ -738,12 +738,12 @@ def main():
         if peer_strip is None:
             step_nccl(k)
             return
-        # Two launches, no collective: the halo push (this strip's boundary rows -> the neighbours'
-        # ghost rows + flag words, NVLink stores) on a high-priority side stream, overlapped with
-        # the residual kernel, whose boundary tiles wait for the neighbours' words and read the
-        # ghost rows locally.  One library call (ldc_residual_peer_step); flow control of the
-        # static-input loop: push(i) waits for this rank's kernel of step i-4, which keeps every
-        # push less than 8 evaluations ahead of the slowest neighbour (9 buffers in rotation).
+        # Three launches, no collective (ONE library call, ldc_residual_peer_step): the halo push
+        # (this strip's boundary rows -> the neighbours' ghost rows + flag words, NVLink stores) and
+        # the strip's edge tiles (which wait for the neighbours' words and read the ghost rows
+        # locally) on two high-priority streams of the library, the rows in between on the launch
+        # stream with the plain kernel.  Flow control of the static-input loop: the pushes of steps
+        # i, i+1 wait for this rank's edge kernel of step i-3 (9 buffers in rotation > 2*3+1).
         peer_launch[k](stream)
 
     def barrier():
