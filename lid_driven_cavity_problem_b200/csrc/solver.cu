@@ -344,8 +344,23 @@ extern "C" int ldc_solver_create(const ldc_grid *g, const ldc_solver_options *op
     A(s->dalloc(&s->X_prev, (size_t)B * n));
     A(s->dalloc(&s->F, (size_t)B * n));
     A(s->dalloc(&s->Y, (size_t)B * n));
-    A(s->dalloc(&s->U_old, (size_t)B * (g->nx - 1) * g->row_count));
-    A(s->dalloc(&s->V_old, (size_t)B * g->nx * g->row_count));
+    // U_old / V_old also stand in as the "old" fields of every coarse level's FD Jacobian (the old
+    // values drop out of the differences): size them for the largest level.  A REPLICATED coarse
+    // level holds the whole coarse grid and can be larger than a thin strip's own fine rows (256^2
+    // over 8 ranks: 8192 fine cells per strip, 16384 cells on the replicated 128^2 level).
+    {
+        size_t old_cells = (size_t)g->nx * g->row_count;
+        if (!(g->row_begin == 0 && g->row_count == g->ny)) {
+            const size_t coarse_whole = ((size_t)g->nx / 2) * ((size_t)g->ny / 2);
+            if (coarse_whole > old_cells) old_cells = coarse_whole;
+        }
+        A(s->dalloc(&s->U_old, (size_t)B * old_cells));
+        A(s->dalloc(&s->V_old, (size_t)B * old_cells));
+        if (rc == LDC_OK) {
+            cudaMemset(s->U_old, 0, sizeof(double) * B * old_cells);
+            cudaMemset(s->V_old, 0, sizeof(double) * B * old_cells);
+        }
+    }
     A(s->dalloc(&s->dt_dev, B));
     A(s->dalloc(&s->bc_dev, B));
     // multigrid hierarchy.  A strip coarsens its own rows; strip boundaries stay aligned because the

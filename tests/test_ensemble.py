@@ -82,6 +82,10 @@ assert [s["steps"] for s in summ] == [k + 1 for k in range(7)], summ
 assert all(s["retries"] == 1 and s["status"] == ensemble.STEADY for s in summ)
 owners = [s["rank"] for s in summ]
 assert owners == [0, 0, 0, 0, 1, 1, 1], owners
+# the same with every rank's cavities cut into two concurrent difficulty groups
+summ2, _ = ensemble.run_ensemble(graphs, distributed=True, groups=2)
+assert [(s["index"], s["steps"], s["retries"], s["rank"]) for s in summ2] == \
+       [(s["index"], s["steps"], s["retries"], s["rank"]) for s in summ], summ2
 dist.barrier(); dist.destroy_process_group()
 sys.stdout.write("rank%dok\n" % rank); sys.stdout.flush()
 '''
@@ -101,16 +105,20 @@ def test_distributed_sharding_gloo_world2(tmp_path):
 
 
 @pytest.mark.gpu
-def test_ensemble_matches_individual_solves():
+@pytest.mark.parametrize("groups", [1, 3])
+def test_ensemble_matches_individual_solves(groups):
     """6 cavities, Re 100..3200 (the last one has to halve dt): lock-step batched solve ==
-    each cavity solved alone (same kernels, masks must not leak between cavities)"""
+    each cavity solved alone (same kernels, masks must not leak between cavities); also with the
+    cavities cut into 3 difficulty groups that run concurrently (own solver, stream and host thread
+    each), handed back in the caller's order (the list is deliberately not sorted by Re)"""
     from lid_driven_cavity_problem_b200.ensemble import run_ensemble, STEADY, RUNNING
     from lid_driven_cavity_problem_b200.nonlinear_solver import solver_builder
     from lid_driven_cavity_problem_b200.time_stepper import run_simulation
     n = 32
-    bcs = [100.0, 200.0, 400.0, 1000.0, 3200.0, 10000.0]
+    bcs = [1000.0, 100.0, 10000.0, 200.0, 3200.0, 400.0]
     graphs = [make_graph([1.0, 1.0, n, n, 1e-2, 1.0, 1.0, bc]) for bc in bcs]
-    summ, (U, V, P) = run_ensemble(graphs, max_steps=6)
+    summ, (U, V, P) = run_ensemble(graphs, max_steps=6, groups=groups)
+    assert [s['bc'] for s in summ] == bcs
     assert len(summ) == 6 and all(s['status'] in (RUNNING, STEADY) for s in summ)
     assert sum(s['retries'] for s in summ) >= 1   # the high-Re cavities have to halve dt
     for b, bc in enumerate(bcs):

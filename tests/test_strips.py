@@ -204,13 +204,14 @@ def test_strip_solver_single_rank_equals_cavity_solver():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,fp32", [(2, 0), (2, 1), (4, 1)])
+@pytest.mark.parametrize("world,fp32", [(2, 0), (2, 1), (4, 1), (8, 1)])
 def test_distributed_strip_solve_equals_single_gpu_solve(world, fp32):
     """The DISTRIBUTED solver path on one GPU: `world` strips of one 128x128 cavity, one thread per
     strip, joined by the in-process transport of tests/thread_transport.py (same three calls as the
     NCCL library).  Exercises the halo rows of fp64 and -- with the mixed-precision cycle -- fp32
     level vectors, the all-reduced norms / Gram-Schmidt coefficients and the all-gather into the
-    replicated coarse levels.  With tight tolerances every Newton solve converges to ~1e-9, so the
+    replicated coarse levels (8 strips: the replicated 64x64 level is larger than a strip's own 16
+    fine rows).  With tight tolerances every Newton solve converges to ~1e-9, so the
     distributed and the single-GPU run must land on the same fields (1e-7 relative), whatever the
     summation order inside the preconditioner."""
     import torch
