@@ -166,7 +166,7 @@ struct Cell2 {   // the two cells of a lane and the cell east of them: raw slots
 // One (column strip, row tile) for one warp.  INTERIOR: no lane touches a wall, the lid, a dummy
 // slot or a missing ghost row, so every mask folds away at compile time.  Everything except
 // `lane` and what is derived from it is warp-uniform.
-template <bool POW2, bool FAST, bool CDS, bool INTERIOR, bool NORM, bool BULK_STORE, int DEPTH>
+template <bool POW2, bool FAST, bool CDS, bool INTERIOR, bool NORM, bool BULK_STORE, int DEPTH, bool FULL = false>
 __device__ __forceinline__ double ring_tile(const ldc_grid &g, const RingPhys &rp, double vol_dt, double bc,
                                             const RingArgs &ra, const double *__restrict__ X,
                                             const double *__restrict__ U_base,
@@ -184,7 +184,7 @@ __device__ __forceinline__ double ring_tile(const ldc_grid &g, const RingPhys &r
     // Narrow grids (nx <= 64, e.g. the 64x64 cavities of a Reynolds ensemble): one strip from wall to
     // wall, lane L owns cells 2L, 2L+1 and lane 0 evaluates the west-wall face itself instead of
     // being the halo lane -- a 64-column row is one warp instead of two half-empty ones.
-    const bool full = !INTERIOR && ra.full_row != 0;
+    constexpr bool full = FULL;   // compile-time: a run-time switch here cost the wall tiles of wide grids 2.5 %
     const int lo = full ? 2 * lane : 2 * lane - 2;    // lane's first column relative to c0
     const int ia = c0 + lo;                           // first cell of the lane; second ia+1, east ia+2
     const bool writer = full ? (lo < cw) : (lane >= 1 && 2 * lane <= cw);   // lanes that own columns of the strip
@@ -553,6 +553,10 @@ residual_ring_kernel(const ldc_grid g, const RingPhys rp, const RingArgs ra, con
     if (interior)
         sq = ring_tile<POW2, FAST, CDS, true, NORM, BULK_STORE, DEPTH>(g, rp, vol_dt, bc, ra, X, U_old, V_old, F, u_off,
                                                                       smem, lane, t.c0, t.cw, t.jl0, t.jl1);
+    else if (!PEER && ra.full_row)
+        sq = ring_tile<POW2, FAST, CDS, false, NORM, BULK_STORE, DEPTH, true>(g, rp, vol_dt, bc, ra, X, U_old, V_old, F,
+                                                                             u_off, smem, lane, t.c0, t.cw, t.jl0,
+                                                                             t.jl1);
     else
         sq = ring_tile<POW2, FAST, CDS, false, NORM, BULK_STORE, DEPTH>(g, rp, vol_dt, bc, ra, X, U_old, V_old, F, u_off,
                                                                        smem, lane, t.c0, t.cw, t.jl0, t.jl1);
