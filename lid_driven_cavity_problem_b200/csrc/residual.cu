@@ -812,7 +812,20 @@ struct MarchPlan {
     int edge_rows = 0;
 };
 
+static MarchPlan plan_march_uncached(const ldc_grid &g);
+// the plan only depends on the grid shape: keep the last one (a 14-20 us kernel should not pay for
+// re-scoring ~60 tile heights and two environment look-ups on every call)
 static MarchPlan plan_march(const ldc_grid &g)
+{
+    struct Key { int nx, rows, batch; };
+    static thread_local Key last_key{0, 0, 0};
+    static thread_local MarchPlan last;
+    if (last_key.nx == g.nx && last_key.rows == g.row_count && last_key.batch == g.batch) return last;
+    last = plan_march_uncached(g);
+    last_key = Key{g.nx, g.row_count, g.batch};
+    return last;
+}
+static MarchPlan plan_march_uncached(const ldc_grid &g)
 {
     const int col_warps = (g.nx + kMarchCols - 1) / kMarchCols;
     const int col_blocks = (col_warps + kMarchWarps - 1) / kMarchWarps;
@@ -1273,7 +1286,7 @@ extern "C" int ldc_residual(const ldc_grid *g, const double *X_dev, const double
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = (getenv("LDC_NO_PDL") == nullptr) ? 1 : 0;
+        cfg.numAttrs = ring_tuning().pdl ? 1 : 0;
         const int rows_arg = pl.rows_per_tile;
 #define LDC_LAUNCH_MARCH(P2, FA, CD)                                                                  \
     LDC_CUDA(cudaLaunchKernelEx(&cfg, residual_march_kernel<P2, FA, CD>, *g, X_dev, U_old_dev, V_old_dev, \
@@ -1413,7 +1426,7 @@ extern "C" int ldc_residual_peer(const ldc_grid *g, const ldc_peer_halo *peer, c
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = ring_tuning().pdl ? 1 : 0;
+    cfg.numAttrs = 0;   // a kernel that contains flag waits is never pre-launched (see ring_launch)
     const int rows_arg = pl.rows_per_tile;
 #define LDC_LAUNCH_PEER(P2, FA, CD)                                                                   \
     LDC_CUDA(cudaLaunchKernelEx(&cfg, residual_march_peer_kernel<P2, FA, CD>, *g, *peer, X_dev,       \
