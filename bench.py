@@ -198,15 +198,17 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-def time_to_converge(max_seconds=120.0):
-    """reference demo recipe at 1024^2 Re=1000 (run_solver.py:42-67): Graph(1,1,n,n,dt=1e-2,rho=1,
-    mi=1,bc=Re), P=U=V=1 start, run_simulation(final_time=None), wall clock around it incl. setup."""
+def time_to_converge(max_seconds=120.0, n=None, re=None, ghia=False):
+    """reference demo recipe (run_solver.py:42-67; default 1024^2 Re=1000): Graph(1,1,n,n,dt=1e-2,
+    rho=1,mi=1,bc=Re), P=U=V=1 start, run_simulation(final_time=None), wall clock around it incl.
+    setup.  ghia=True adds the centre-line comparison with Ghia, Ghia & Shin as numbers."""
     import torch
     from lid_driven_cavity_problem_b200.nonlinear_solver import cuda_solver_wrapper
     from lid_driven_cavity_problem_b200.staggered_grid import Graph
     from lid_driven_cavity_problem_b200.time_stepper import run_simulation
+    n, re = n or NX, re or RE
     wrapper = cuda_solver_wrapper.CudaSolverWrapper(None)
-    graph = Graph(1.0, 1.0, NX, NY, 1e-2, 1.0, 1.0, RE)
+    graph = Graph(1.0, 1.0, n, n, 1e-2, 1.0, 1.0, re)
     steps = []
     torch.cuda.synchronize()
     t0 = time.time()
@@ -216,19 +218,42 @@ def time_to_converge(max_seconds=120.0):
         if time.time() - t0 > max_seconds:
             raise TimeoutError()
     status = 'converged (reference steady test: max|U-U_old|/bc < 1e-6)'
+    result = None
     try:
-        run_simulation(graph, None, wrapper.solve, on_step=on_step)
+        result = run_simulation(graph, None, wrapper.solve, on_step=on_step)
     except TimeoutError:
         status = 'stopped after %.0f s' % max_seconds
     torch.cuda.synchronize()
     sec = time.time() - t0
+    out = {"grid": "%dx%d" % (n, n), "Re": re, "seconds": round(sec, 3), "status": status,
+           "time_steps": len(steps), "newton_iterations": wrapper.total_newton_iterations,
+           "krylov_iterations": wrapper.total_linear_iterations,
+           "residual_evaluations": wrapper.total_function_evaluations,
+           "fd_jacobian_launches": wrapper.total_jacobian_evaluations,
+           "pseudo_time": steps[-1] if steps else 0.0}
+    if ghia and result is not None:
+        from lid_driven_cavity_problem_b200 import validation
+        cmp_ = validation.compare_with_ghia(result, re)
+        out["ghia"] = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in cmp_.items()
+                       if k in ('rms_u', 'rms_v', 'max_u', 'max_v', 'rms_u_as_plotted', 'rms_v_as_plotted', 'source')}
     wrapper.close()
-    return {"grid": "%dx%d" % (NX, NY), "Re": RE, "seconds": round(sec, 3), "status": status,
-            "time_steps": len(steps), "newton_iterations": wrapper.total_newton_iterations,
-            "krylov_iterations": wrapper.total_linear_iterations,
-            "residual_evaluations": wrapper.total_function_evaluations,
-            "fd_jacobian_launches": wrapper.total_jacobian_evaluations,
-            "pseudo_time": steps[-1] if steps else 0.0}
+    return out
+
+
+def baseline_configs_table():
+    """the single-GPU configurations of BASELINE.json that are not the headline: [0] 100^2 Re=1000
+    (Ghia validation case, centre-line differences as numbers), [1] 256^2 Re=1000 pseudo-transient
+    run through the time stepper, [2] 1024^2 Re=3200 steady coupled solve -- all with the reference
+    recipe, wall clock incl. solver setup."""
+    rows = []
+    time_to_converge(30.0, 64, 100.0)                                  # module load / first-use costs
+    for label, n, re, ghia in (("config 0: 100x100 Re=1000 (Ghia validation)", 100, 1000.0, True),
+                               ("config 1: 256x256 Re=1000 pseudo-transient", 256, 1000.0, False),
+                               ("config 2: 1024x1024 Re=3200 steady", 1024, 3200.0, False)):
+        r = time_to_converge(90.0, n, re, ghia)
+        r["config"] = label
+        rows.append(r)
+    return rows
 
 
 def _time_loop(fn, n_sets, iters, warmup=3):
@@ -345,6 +370,13 @@ def cpu_solve_lower_bound(gpu_seconds, factor=60.0, min_budget=45.0, max_budget=
     left = lambda: budget - (time.time() - t_start)   # noqa: E731
     g = Graph(1.0, 1.0, nx, ny, 1e-2, 1.0, 1.0, RE)
     mask = orc.jacobian_mask_arrays(nx, ny, 3)
+    try:     # F(X) itself: the reference's own C++-OpenMP residual where it was built
+        ref = orc.ref_module()
+        residual = lambda X_, g_: np.asarray(ref.residual_function_omp(X_, g_))   # noqa: E731
+        residual_kind = "reference C++-OpenMP residual (oracle/_ref)"
+    except Exception:
+        residual = lambda X_, g_: orc.residual_function(X_, g_, nthreads=0)       # noqa: E731
+        residual_kind = "oracle C residual"
     U, V, P = (np.array(a, dtype=np.float64) for a in (g.ns_x_mesh.phi, g.ns_y_mesh.phi, g.pressure_mesh.phi))
     dt, t_it = 1e-2, None
     steps = retries = newton = gm = 0
@@ -354,7 +386,7 @@ def cpu_solve_lower_bound(gpu_seconds, factor=60.0, min_budget=45.0, max_budget=
         g.dt = dt
         g.ns_x_mesh.phi_old, g.ns_y_mesh.phi_old, g.pressure_mesh.phi_old = U, V, P
         X = orc.create_X(U, V, P, g)
-        F = orc.residual_function(X, g, nthreads=0)
+        F = residual(X, g)
         fnorm = float(np.linalg.norm(F))
         ttol, reason = fnorm * 1e-4, (2 if fnorm < 1e-4 else 0)
         it = 0
@@ -387,7 +419,7 @@ def cpu_solve_lower_bound(gpu_seconds, factor=60.0, min_budget=45.0, max_budget=
                     reason = -3
                 break
             X = X - y
-            F = orc.residual_function(X, g, nthreads=0)
+            F = residual(X, g)
             it += 1
             newton += 1
             fnorm, ynorm, xnorm = (float(np.linalg.norm(v)) for v in (F, y, X))
@@ -413,6 +445,7 @@ def cpu_solve_lower_bound(gpu_seconds, factor=60.0, min_budget=45.0, max_budget=
     out = {"kind": "port (oracle restatement of the reference's PETSc configuration: SNES newtonls/basic, "
                    "21-colour FD Jacobian, left-preconditioned GMRES(30) + ILU(0), ksp_rtol 1e-5, inside the "
                    "reference's time stepper; PETSc/petsc4py are not installable)",
+           "residual": residual_kind,
            "grid": "%dx%d" % (nx, ny), "cores": os.cpu_count(), "deadline_s": round(budget, 1),
            "seconds_spent": round(spent, 2), "converged": finished, "time_steps_done": steps, "dt_halvings": retries,
            "newton_iterations_done": newton, "gmres_iterations_done": gm,
@@ -962,6 +995,10 @@ def main():
         except Exception as e:
             line["named_sizes"] = {"error": repr(e)}
     if world == 1 and not args.no_solve:
+        try:
+            line["baseline_configs"] = baseline_configs_table()
+        except Exception as e:
+            line["baseline_configs"] = {"error": repr(e)}
         try:
             line["time_to_converge"] = time_to_converge()
             if not args.no_cpu:
