@@ -78,7 +78,8 @@ LDC_API int ldc_residual(const ldc_grid *g, const double *X_dev, const double *U
  * U_old_host[(nx-1)*ny], V_old_host[nx*(ny-1)] are read, F_host[3*nx*ny] is written; any
  * pageable memory.  The call is a copy pipeline over row blocks: multi-threaded staging into
  * pinned memory, H2D, the strip form of ldc_residual per block, D2H and copy-out overlap, with
- * both PCIe directions busy at once.  Synchronous (F_host is complete on return); buffers,
+ * both PCIe directions busy at once; a page-locked F_host (cudaHostAlloc / cudaHostRegister)
+ * receives the D2H copies directly.  Synchronous (F_host is complete on return); buffers,
  * streams and copy threads are created once per process; calls are serialised.  batch must be
  * 1, dt_dev / bc_dev NULL.  LDC_HOST_COPY_THREADS overrides the copy-thread count (default:
  * min(8, cores / LOCAL_WORLD_SIZE)). */

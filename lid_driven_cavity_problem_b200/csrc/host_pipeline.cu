@@ -11,7 +11,8 @@
 //                   have arrived                                               (ldc_residual, strip form)
 //   stream `out`  : the block's F rows -> pinned staging                       (D2H DMA, full duplex
 //                                                                               with the H2D of later blocks)
-//   host threads  : staging -> the caller's F                                  (memcpy, parallel)
+//   host threads  : staging -> the caller's F                                  (memcpy, parallel; skipped
+//                                                                               when F is page-locked already)
 // so the PCIe link is busy in both directions and the host copies hide behind the DMAs.
 // Staging buffers, device buffers, streams, events and the copy threads are created once per
 // process and reused (grow-only); calls are serialised by a mutex.
@@ -225,6 +226,16 @@ extern "C" int ldc_residual_host(const ldc_grid *g, const double *X_host, const 
     LDC_REQUIRE(X_host != F_host, "ldc_residual_host: F must not alias X");
     const long nx = g->nx, ny = g->ny;
     const size_t n3 = (size_t)3 * nx * ny;
+    // A result buffer that is already page-locked (the Python forwarder hands out numpy arrays backed
+    // by torch's pinned-memory cache) receives the D2H copies directly: no staging, no copy-out.
+    bool f_pinned = false;
+    {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, F_host) == cudaSuccess)
+            f_pinned = attr.type == cudaMemoryTypeHost;
+        else
+            cudaGetLastError();   // pageable memory is not an error here
+    }
     HostPipeline &p = g_pipe;
     std::lock_guard<std::mutex> guard(p.lock);
     // LDC_HOST_PROFILE=1: host-clock marks of the pipeline phases on stderr (us since call entry)
@@ -260,8 +271,8 @@ extern "C" int ldc_residual_host(const ldc_grid *g, const double *X_host, const 
             return rc;
         LDC_CUDA(cudaEventRecord(p.ev_run[b], p.s_run));
         LDC_CUDA(cudaStreamWaitEvent(p.s_out, p.ev_run[b], 0));
-        LDC_CUDA(cudaMemcpyAsync(p.pin_out + 3 * nx * r0, p.dF + 3 * nx * r0, sizeof(double) * 3 * nx * (r1 - r0),
-                                 cudaMemcpyDeviceToHost, p.s_out));
+        LDC_CUDA(cudaMemcpyAsync((f_pinned ? F_host : p.pin_out) + 3 * nx * r0, p.dF + 3 * nx * r0,
+                                 sizeof(double) * 3 * nx * (r1 - r0), cudaMemcpyDeviceToHost, p.s_out));
         LDC_CUDA(cudaEventRecord(p.ev_out[b], p.s_out));
         return LDC_OK;
     };
@@ -295,7 +306,8 @@ extern "C" int ldc_residual_host(const ldc_grid *g, const double *X_host, const 
         const long r0 = row_of(b), r1 = row_of(b + 1);
         LDC_CUDA(cudaEventSynchronize(p.ev_out[b]));
         mark("D2H landed, block", b);
-        p.pool->copy(F_host + 3 * nx * r0, p.pin_out + 3 * nx * r0, sizeof(double) * 3 * nx * (r1 - r0));
+        if (!f_pinned)
+            p.pool->copy(F_host + 3 * nx * r0, p.pin_out + 3 * nx * r0, sizeof(double) * 3 * nx * (r1 - r0));
     }
     mark("copied out", nb);
     return LDC_OK;

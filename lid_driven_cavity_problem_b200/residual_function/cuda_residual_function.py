@@ -30,6 +30,7 @@ except RuntimeError:
     raise RuntimeError("CUDA module is not compiled.")
 
 _staging = {}
+_PINNED_RESULT_LIMIT = 512 << 20   # bytes
 
 
 def _pinned(name, n, torch):
@@ -124,7 +125,15 @@ def residual_function(X, graph):
     Xh = _as_f64('X', X, n)
     Uh = _as_f64('U_old', graph.ns_x_mesh.phi_old, (nx - 1) * ny)
     Vh = _as_f64('V_old', graph.ns_y_mesh.phi_old, nx * (ny - 1))
-    result = np.empty(n, dtype=np.float64)      # freshly allocated, like the reference backends
+    # Freshly allocated for every call, like the reference backends -- but out of torch's cache of
+    # page-locked host memory, so that the D2H copies land in the result itself (no staging buffer,
+    # no 25 MB copy-out per 1024^2 call).  The numpy array keeps the block alive; when the caller
+    # drops it the block returns to the cache.  Large results (and LDC_PAGEABLE_RESULT=1) use
+    # ordinary memory: page-locked memory is a limited resource.
+    if 8 * n <= _PINNED_RESULT_LIMIT and not os.environ.get('LDC_PAGEABLE_RESULT'):
+        result = torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()
+    else:
+        result = np.empty(n, dtype=np.float64)
     g = _native.grid_from_graph(graph)
     rc = _native.lib().ldc_residual_host(g, Xh.ctypes.data, Uh.ctypes.data, Vh.ctypes.data, result.ctypes.data, 0)
     _native.check(rc, 'ldc_residual_host')
