@@ -125,12 +125,12 @@ def residual_function(X, graph):
     Xh = _as_f64('X', X, n)
     Uh = _as_f64('U_old', graph.ns_x_mesh.phi_old, (nx - 1) * ny)
     Vh = _as_f64('V_old', graph.ns_y_mesh.phi_old, nx * (ny - 1))
-    # Freshly allocated for every call, like the reference backends -- but out of torch's cache of
-    # page-locked host memory, so that the D2H copies land in the result itself (no staging buffer,
-    # no 25 MB copy-out per 1024^2 call).  The numpy array keeps the block alive; when the caller
-    # drops it the block returns to the cache.  Large results (and LDC_PAGEABLE_RESULT=1) use
-    # ordinary memory: page-locked memory is a limited resource.
-    if 8 * n <= _PINNED_RESULT_LIMIT and not os.environ.get('LDC_PAGEABLE_RESULT'):
+    # Freshly allocated for every call, like the reference backends.  LDC_PINNED_RESULT=1 takes the
+    # array out of torch's cache of page-locked host memory instead, so that the D2H copies land in
+    # the result itself (ldc_residual_host detects a page-locked F): 10 % faster for a caller that
+    # drops each result before the next call (1.34 vs 1.48 ms per 1024^2 call), 20 % SLOWER for one
+    # that still holds the previous result (bench.py's loop: 1.82 vs 1.53 ms) -- hence opt-in.
+    if os.environ.get('LDC_PINNED_RESULT') and 8 * n <= _PINNED_RESULT_LIMIT:
         result = torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()
     else:
         result = np.empty(n, dtype=np.float64)

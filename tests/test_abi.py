@@ -125,7 +125,23 @@ def test_argument_validation_happens_before_any_device_work():
     g.batch = 1
     assert refused(lib.ldc_residual_peer_push(g, ph, px, None), b'neighbour strip exists')
     assert lib.ldc_residual_work_doubles(g) > 0
+    # the host-buffer entry point and the helpers added in round 2
+    assert refused(lib.ldc_residual_host(g, None, px, px, pf, 0), b'null host pointer')
+    assert refused(lib.ldc_residual_host(g, px, px, px, px, 0), b'must not alias')
+    g.row_begin, g.row_count = 2, 4
+    assert refused(lib.ldc_residual_host(g, px, px, px, pf, 0), b'needs the full grid')
+    g.row_begin, g.row_count = 0, 8
+    g.batch = 2
+    assert refused(lib.ldc_residual_host(g, px, px, px, pf, 0), b'one cavity per call')
+    g.batch = 1
+    assert refused(lib.ldc_peer_ctx_create(0, ctypes.byref(ctypes.c_void_p())), b'lag must be in')
+    assert refused(lib.ldc_solver_plan_levels(g, None, None, None), b'null argument')
+    assert refused(lib.ldc_solver_time_ops(None, 1, None, None), b'bad argument')
+    assert refused(lib.ldc_solver_set_keep_diverged(None, 1), b'null solver')
     if not torch.cuda.is_available():
+        rc = lib.ldc_residual_host(g, px, px, px, pf, 0)
+        assert rc == -2 and b'CUDA error' in lib.ldc_last_error()
+        assert not F.any()
         rc = lib.ldc_residual(g, px, px, px, pf, None, None, 0, None)
         assert rc == -2 and b'CUDA error' in lib.ldc_last_error()
         assert not F.any()                  # nothing was computed anywhere
