@@ -51,3 +51,25 @@ def test_product_arm_has_no_cpu_fallback():
     r = _run(['--steps', '1', '--warmup', '1', '--no-solve', '--no-cpu', '--no-tables'])
     assert r.returncode != 0
     assert r.stdout.strip() == ''          # no number without the device
+
+
+def test_cpu_path_under_deadline_runs_the_reference_recipe():
+    """bench.py's CPU arm for time-to-converge (the oracle's restatement of the reference's PETSc
+    configuration inside the reference's stepper, F evaluated by the reference's own C++-OpenMP
+    residual where oracle/_ref is built): on a 16x16 grid it reaches the steady state well inside
+    the deadline and reports a speed-up; with a deadline it cannot meet it reports how far it got
+    and a lower bound instead."""
+    sys.path.insert(0, REPO)
+    import bench
+    done = bench.cpu_solve_lower_bound(0.05, factor=1.0, min_budget=20.0, max_budget=20.0, nx=16, ny=16)
+    assert done['converged'] and done['time_steps_done'] >= 3 and done['newton_iterations_done'] >= 3
+    assert done['speedup'] > 0 and 'progress_at_deadline' not in done
+    # the same path as the oracle's own driver (which the stepper-trace goldens pin on the reference)
+    from oracle import ldc_oracle as orc
+    from lid_driven_cavity_problem_b200.staggered_grid import Graph
+    _, hist = orc.run_simulation(Graph(1.0, 1.0, 16, 16, 1e-2, 1.0, 1.0, bench.RE), None, linear='gmres_ilu0')
+    assert len(hist) == done['time_steps_done']
+    assert sum(h.iterations for h in hist) == done['newton_iterations_done']
+    cut = bench.cpu_solve_lower_bound(0.05, factor=1.0, min_budget=0.02, max_budget=0.02, nx=48, ny=48)
+    assert not cut['converged'] and cut['speedup_greater_than'] > 0
+    assert cut['cpu_time_to_converge_s_greater_than'] >= 0.02 and 'time step' in cut['progress_at_deadline']
