@@ -126,7 +126,7 @@ class PeerStripResidual(object):
 
     def residual(self, k, U_old, V_old, F, stream=None, norm2=None, work=None, push_stream=None):
         """F <- residual of the strip's owned rows of X buffer ``k`` (push + kernel); every strip must
-        make the same sequence of calls (the epoch counter is the handshake)."""
+        make the same sequence of calls (the evaluation number `epoch` is what the flag words carry)."""
         self.bind(k, U_old, V_old, F, norm2, work)(stream if stream is not None else _native.current_stream(),
                                                    push_stream)
 

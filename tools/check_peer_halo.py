@@ -1,9 +1,11 @@
-"""Multi-GPU check of the fused-halo strip residual (ldc_residual_peer) on uneven row strips.
+"""Multi-GPU check of the collective-free strip residual (ldc_residual_peer_push +
+ldc_residual_peer) on uneven row strips.
 
     python -m torch.distributed.run --nproc-per-node 4 --master-addr 127.0.0.1 tools/check_peer_halo.py --nx 250 --ny 203
 
-Every rank evaluates its strip through peer-mapped neighbour rows and compares it, bit for bit,
-with its slice of the full-grid residual (ldc_residual on the same GPU).  Repeats for a few
+Every rank pushes its boundary rows into the neighbours' ghost rows (peer-mapped memory), evaluates
+its strip once their flag words arrive and compares it, bit for bit, with its slice of the
+full-grid residual (ldc_residual on the same GPU).  Repeats for a few
 epochs with changed X (an all-reduce in between keeps the buffers safe to overwrite).
 """
 import argparse
