@@ -785,7 +785,7 @@ def main():
         # the strip's edge tiles (which wait for the neighbours' words and read the ghost rows
         # locally) on two high-priority streams of the library, the rows in between on the launch
         # stream with the plain kernel.  Flow control of the static-input loop: the pushes of steps
-        # i, i+1 wait for this rank's edge kernel of step i-3 (9 buffers in rotation > 2*3+1).
+        # i, i+1 wait for this rank's edge kernel of step i-3 or i-4 (9 buffers in rotation = 2*3+3).
         peer_launch[k](stream)
 
     def barrier():

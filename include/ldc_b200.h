@@ -133,10 +133,11 @@ LDC_API int ldc_residual_peer(const ldc_grid *g, const ldc_peer_halo *peer, cons
  * (bench.py does so once, in front of the event that ends a timed region).  Meant for loops over
  * rotating X buffers whose contents are final before the loop starts: the context's streams are
  * not ordered after work queued on `stream`.  Flow control is amortised over two evaluations:
- * the pushes of evaluations i, i+1 (i even) wait for this strip's edge kernel of evaluation
- * i-lag.  That edge kernel needed the neighbours' push(i-lag), which waited for their edge kernels
- * of evaluation <= i-2*lag, so a ghost row is never overwritten while a neighbour still reads it
- * as long as more than 2*lag+1 X buffers rotate.  A caller whose X is
+ * the pushes of evaluations i, i+1 (i even) wait for this strip's newest recorded edge kernel that
+ * is at least `lag` evaluations old (evaluation i-lag or i-lag-1).  That edge kernel needed the
+ * neighbours' pushes of the same evaluation, which waited for their edge kernels of evaluation
+ * >= i-2*lag-2, so a ghost row is never overwritten while a neighbour still reads it as long as
+ * at least 2*lag+3 X buffers rotate.  A caller whose X is
  * produced on `stream` between evaluations uses ldc_residual_peer_push / ldc_residual_peer with
  * its own event. */
 typedef struct ldc_peer_ctx ldc_peer_ctx;

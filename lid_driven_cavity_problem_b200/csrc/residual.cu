@@ -1532,19 +1532,21 @@ extern "C" int ldc_residual_peer_step(ldc_peer_ctx *c, const ldc_grid *g, const 
     const int slot = (int)(i % ldc_peer_ctx::kEvents);
     static const int dbg = ring_env_int("LDC_PEER_DEBUG", 0);
     cudaStream_t s = (cudaStream_t)stream;
-    // Flow control, amortised: an event is recorded behind the edge kernel of every `stride`-th
-    // evaluation, and the pushes of evaluations i .. i+stride-1 (i a multiple of stride) wait for the
-    // edge kernel of evaluation i-lag.  That kernel needed the neighbours' push(i-lag), which waited
-    // for THEIR edge kernels of evaluation <= i-2*lag: when push(i+stride-1) overwrites a ghost row,
-    // the neighbour has finished reading every ghost row up to evaluation i-2*lag, so rotating more
-    // than 2*lag+stride-1 X buffers is safe (lag 4, stride 2: 9 = bench.py's rotation).  The event
-    // is `lag` evaluations old and never holds a push up in steady state.  Why amortised, and why
-    // nothing ties the push / edge streams to `stream`: a 14 us kernel leaves ~1 us per driver
-    // call (3 us per launch on this host); with a record and two waits per step the HOST needed
-    // 15 us per step.
+    // Flow control, amortised: an event is recorded behind the edge kernel of every second
+    // evaluation (the even ones), and the pushes of evaluations i, i+1 (i even) wait for the newest
+    // recorded edge kernel that is at least `lag` evaluations old: j = (i-lag) rounded down to even,
+    // so i-lag-1 <= j <= i-lag.  Edge kernel j needed the neighbours' push(j), which waited for THEIR
+    // edge kernels of evaluation >= j-lag-1 >= i-2*lag-2: when push(i+1) overwrites a ghost row, the
+    // neighbour has finished reading every ghost row up to evaluation i-2*lag-2, so rotating at least
+    // 2*lag+3 X buffers is safe (lag 3: 9 = bench.py's rotation).  The event is at least `lag`
+    // evaluations old and never holds a push up in steady state.  Why amortised, and why nothing
+    // ties the push / edge streams to `stream`: a 14 us kernel leaves ~1 us per driver call (~4 us
+    // per launch on this host); with a record and two waits per step the HOST needed 15 us per step.
     const int stride = 2;
-    if (i % stride == 0 && i >= c->lag && !(dbg & 64))
-        LDC_CUDA(cudaStreamWaitEvent(c->side, c->edge_events[(i - c->lag) % ldc_peer_ctx::kEvents], 0));
+    if (i % stride == 0 && i >= c->lag + 1 && !(dbg & 64)) {
+        const long j = ((i - c->lag) / stride) * stride;   // even, recorded, >= 0
+        LDC_CUDA(cudaStreamWaitEvent(c->side, c->edge_events[j % ldc_peer_ctx::kEvents], 0));
+    }
     const bool has_prev = peer->prev_ghost != nullptr, has_next = peer->next_ghost != nullptr;
     const int n_edges = (has_prev ? 1 : 0) + (has_next ? 1 : 0);
     const int edge = ring_eligible(*g, X_dev, U_old_dev, V_old_dev, F_dev) ? ring_edge_rows(*g, n_edges) : 0;

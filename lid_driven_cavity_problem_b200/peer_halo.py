@@ -91,10 +91,10 @@ class PeerStripResidual(object):
         """``launch(stream)``: ONE library call per evaluation (ldc_residual_peer_step) that puts the
         push and the strip's edge tiles on the library's two high-priority streams and the rows in
         between on ``stream``; ``join(stream)`` before F is consumed.  For loops over rotating X
-        buffers that are final before the loop starts; needs ``n_sets > 2*lag + 1``
+        buffers that are final before the loop starts; needs ``n_sets >= 2*lag + 3``
         (see include/ldc_b200.h)."""
-        if self.n_sets <= 2 * lag + 1:
-            raise ValueError("overlapped evaluation needs more than 2*lag+1 rotating X buffers")
+        if self.n_sets < 2 * lag + 3:
+            raise ValueError("overlapped evaluation needs at least 2*lag+3 rotating X buffers")
         if self._ctx is None:
             self._ctx = ctypes.c_void_p()
             _native.check(self.lib.ldc_peer_ctx_create(lag, ctypes.byref(self._ctx)), 'ldc_peer_ctx_create')
