@@ -133,6 +133,57 @@ def test_peer_halo_region_layout_and_handshake_addresses(monkeypatch):
         peer_halo.PeerStripResidual(g, local, 0, 0, 0, rows_max, n_sets)
 
 
+def test_overlapped_strip_step_host_contract(monkeypatch):
+    """bind_overlapped: one ldc_residual_peer_step per evaluation with a strictly increasing epoch, a
+    context created once, join() forwarded, and the rotation rule of the amortised flow control
+    (at least 2*lag+3 X buffers, include/ldc_b200.h) enforced before anything is launched."""
+    import ctypes
+    from lid_driven_cavity_problem_b200 import _native, peer_halo
+    nx, rows_max = 12, 10
+    g = _native.LdcGrid()
+    g.nx, g.ny, g.row_begin, g.row_count, g.batch = nx, 27, 7, 10, 1
+    log = []
+
+    class FakeLib(object):
+        @staticmethod
+        def ldc_peer_ctx_create(lag, out_ref):
+            out_ref._obj.value = 0xC0FFEE
+            log.append(('create', lag))
+            return 0
+
+        @staticmethod
+        def ldc_residual_peer_step(ctx, grid, ph_ref, X, U, V, F, n2, work, stream):
+            log.append(('step', ctx.value, ph_ref._obj.epoch, X.value, stream.value))
+            return 0
+
+        @staticmethod
+        def ldc_peer_ctx_join(ctx, stream):
+            log.append(('join', ctx.value, stream.value))
+            return 0
+
+        @staticmethod
+        def ldc_peer_ctx_destroy(ctx):
+            log.append(('destroy', ctx.value))
+    monkeypatch.setattr(_native, 'lib', lambda: FakeLib)
+    local, prev, nxt = 0x100000, 0x200000, 0x300000
+    few = peer_halo.PeerStripResidual(g, local, prev, nxt, prev_rows=7, rows_max=rows_max, n_sets=8)
+    with pytest.raises(ValueError, match='2\\*lag\\+3'):
+        few.bind_overlapped(0, None, None, None, lag=3)
+    assert log == []
+    strip = peer_halo.PeerStripResidual(g, local, prev, nxt, prev_rows=7, rows_max=rows_max, n_sets=9)
+    launches = [strip.bind_overlapped(k, None, None, None, lag=3) for k in range(9)]
+    for k in (0, 1, 2, 0):
+        launches[k](ctypes.c_void_p(5))
+    strip.join(ctypes.c_void_p(5))
+    strip.close()
+    strip.close()
+    assert log[0] == ('create', 3) and [e[0] for e in log].count('create') == 1
+    steps = [e for e in log if e[0] == 'step']
+    assert [e[2] for e in steps] == [1, 2, 3, 4] and all(e[1] == 0xC0FFEE and e[4] == 5 for e in steps)
+    assert [e[3] for e in steps] == [strip.x_address(k) for k in (0, 1, 2, 0)]
+    assert log[-2:] == [('join', 0xC0FFEE, 5), ('destroy', 0xC0FFEE)]
+
+
 _WORKER = r'''
 import os, sys
 sys.path.insert(0, os.environ["LDC_REPO"])
