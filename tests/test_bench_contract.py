@@ -70,6 +70,7 @@ def test_cpu_path_under_deadline_runs_the_reference_recipe():
     _, hist = orc.run_simulation(Graph(1.0, 1.0, 16, 16, 1e-2, 1.0, 1.0, bench.RE), None, linear='gmres_ilu0')
     assert len(hist) == done['time_steps_done']
     assert sum(h.iterations for h in hist) == done['newton_iterations_done']
+    assert sum(h.function_evaluations for h in hist) == done['residual_evaluations_done']
     cut = bench.cpu_solve_lower_bound(0.05, factor=1.0, min_budget=0.02, max_budget=0.02, nx=48, ny=48)
     assert not cut['converged'] and cut['speedup_greater_than'] > 0
     assert cut['cpu_time_to_converge_s_greater_than'] >= 0.02 and 'time step' in cut['progress_at_deadline']
