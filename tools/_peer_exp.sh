@@ -1,3 +1,5 @@
+# NOTE: experiment log. Bits 2, 4, 8, 32 (fence / polling variants) existed only in the builds these runs used;
+# the library keeps 1 (no flag waits), 16 (no push), 64 (no flow-control events), 256 (single-kernel fallback).
 # breakdown of the N=2 fused step (LDC_PEER_DEBUG bits: 1 no flag waits, 16 no push, 32 single peer kernel, 64 no events)
 python -m pytest tests/test_cuda_kernels.py -m gpu -q -x -k "peer" 2>&1 | tail -30
 for k in 200; do

@@ -1,3 +1,5 @@
+# NOTE: experiment log of the 2-GPU strip-step runs quoted in DESIGN.md section 7 (LDC_PEER_DEBUG bits 512 / 1024 /
+# 2048 / 4096 and LDC_PEER_NO_HELPER existed only in the builds those runs used).
 run() {
     env "$@" python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps $K --warmup 5 --no-cpu --no-strips --no-ensemble 2>/dev/null | python -c "
 import sys,json
